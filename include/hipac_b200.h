@@ -1,0 +1,122 @@
+/*
+ * hipac_b200.h -- C ABI of the B200-native HiPAC hot path (libhipac_b200.so).
+ *
+ * The reference (anacarsi/ss25_Hierarchical_Multiscale_Image_Classification) has no FFI
+ * or plugin layer: its boundary is plain Python functions.  Each entry
+ * point below names the reference code it replaces; the Python mirror of the
+ * reference interface (package ss25_hierarchical_multiscale_image_classification_b200)
+ * binds these symbols with ctypes.  INTEGRATION.md shows the reference-side stub.
+ *
+ * Conventions
+ *   - every pointer named d_* is DEVICE memory owned by the caller (PyTorch),
+ *     h_* is host memory; the library allocates no persistent device memory
+ *     except small constant tables.
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*).
+ *   - return 0 on success, negative on error; hipac_last_error() gives the text.
+ *     Nothing throws across the ABI.
+ */
+#ifndef HIPAC_B200_H
+#define HIPAC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HIPAC_ABI_VERSION 1
+
+/* batch layouts written by hipac_tile_scan / consumed by hipac_resnet18_forward */
+#define HIPAC_LAYOUT_NHWC3_BF16 1 /* bf16 [N,224,224,3], (u8/255-mean)/std, the reference's tensor (src/main.py:815-816) in NHWC */
+#define HIPAC_LAYOUT_S2D16_BF16 2 /* bf16 [N,112,112,16]: 2x2 space-to-depth of the above, ch=(dy*2+dx)*3+c, 12..15 zero (conv1 operand) */
+
+/* stage-1 algorithm selector */
+#define HIPAC_SCAN_AUTO   0 /* fused read-once path when stride %% (P/224) == 0, else direct */
+#define HIPAC_SCAN_DIRECT 1 /* one window reduction + one resample per patch (any stride) */
+#define HIPAC_SCAN_FUSED  2 /* single streaming pass over the level image (error if not applicable) */
+
+const char* hipac_last_error(void);
+int hipac_abi_version(void);
+
+/* ---------------------------------------------------------------------------------------
+ * Stage 1: multiscale patch extraction of ONE level image resident in HBM.
+ * Replaces the hot loop of extract_patches (reference src/main.py:682-727): candidate grid
+ * x in range(0,W,S), y in range(0,H,S) (x outer), white padding of border patches (688-703),
+ * tissue test mean>240 -> reject (718-720, integer form sum <= 240*3*P*P), lesion label
+ * any(mask[y:y+P,x:x+P]>0) (705-716), and -- instead of the PNG round trip -- the
+ * Resize((224,224)) + ToTensor + Normalize of src/main.py:812-818 (Pillow-exact antialiased
+ * bilinear in 22-bit fixed point, two uint8 passes).
+ *
+ *   d_rgb        uint8 [H][pitch_bytes], 3 bytes per pixel (RGB), level-L image
+ *   d_mask       uint8 [H][mask_pitch] rasterised lesion mask (>0 = lesion) or NULL (all "normal")
+ *   P, S         patch size (1792>>level) and stride (reference CLI: 224)
+ *   iy_begin/end candidate grid rows y/S in [iy_begin, iy_end)  (the multi-GPU shard unit)
+ *   outputs      survivors in the reference's emission order (x outer, y inner):
+ *     d_coords   int32 [capacity][2] (x, y) level-L pixel coordinates
+ *     d_labels   uint8 [capacity]    1 = tumor, 0 = normal
+ *     d_batch_u8 uint8 [capacity][224][224][3] Pillow-exact resized patch, or NULL
+ *     d_batch    bf16 batch in `layout`, or NULL
+ *     d_count    int32 [2]: {survivors, candidates}; survivors may exceed capacity, in which
+ *                case only the first `capacity` are written (caller re-runs with a smaller row range)
+ *   d_workspace  >= hipac_tile_scan_workspace_bytes(...) bytes, 256-byte aligned
+ * ------------------------------------------------------------------------------------- */
+size_t hipac_tile_scan_workspace_bytes(int H, int W, int P, int S, int iy_begin, int iy_end, int mode);
+
+int hipac_tile_scan(const uint8_t* d_rgb, int H, int W, int64_t pitch_bytes,
+                    const uint8_t* d_mask, int64_t mask_pitch,
+                    int P, int S, int iy_begin, int iy_end,
+                    int32_t* d_coords, uint8_t* d_labels,
+                    uint8_t* d_batch_u8, void* d_batch, int layout,
+                    int32_t* d_count, int capacity,
+                    void* d_workspace, size_t workspace_bytes,
+                    int mode, void* stream);
+
+/* Pillow coefficient tables used by the kernels (known-answer hook for the CPU tests; no GPU needed).
+ * scale in {2,4,8}; writes interior[2*scale], left_edge[3*scale/2], right_edge[3*scale/2] (22-bit fixed point). */
+int hipac_pillow_coeffs(int scale, int32_t* h_interior, int32_t* h_left, int32_t* h_right);
+
+/* float32 -> bf16 bits of the ToTensor+Normalize LUT, [256][3] (known-answer hook, host only). */
+int hipac_normalize_lut_bf16(uint16_t* h_lut);
+
+/* ---------------------------------------------------------------------------------------
+ * Stage 2: ResNet18 forward (reference src/models/resnet.py:22-77 = torchvision resnet18
+ * trunk, eval-mode BN, global average pool [+ Linear(512,k)]) on a bf16 batch.
+ * ------------------------------------------------------------------------------------- */
+
+/* Number of fp32 tensors hipac_resnet18_pack expects and their order: see INTEGRATION.md
+ * (conv weight, bn weight, bn bias, bn running_mean, bn running_var per conv, network order;
+ * then fc weight [k][512] and fc bias [k], or NULL,NULL for the headless feature extractor). */
+#define HIPAC_RESNET18_NUM_CONVS 20
+#define HIPAC_RESNET18_NUM_TENSORS (HIPAC_RESNET18_NUM_CONVS * 5 + 2)
+
+size_t hipac_resnet18_packed_bytes(int num_classes);
+
+/* Fold eval-mode BatchNorm into the conv weights (fp32), convert to the bf16 K-major layouts the
+ * implicit-GEMM kernels read, write the blob to HOST memory `h_packed` (caller uploads it). */
+int hipac_resnet18_pack(const float* const* h_tensors, int num_tensors, int num_classes, float bn_eps,
+                        void* h_packed, size_t packed_bytes);
+
+size_t hipac_resnet18_workspace_bytes(int n_patches, int chunk);
+
+/* d_batch: bf16 batch of n_patches in `layout` (HIPAC_LAYOUT_S2D16_BF16 is the native one).
+ * d_feats: float32 [n][512]; d_logits: float32 [n][num_classes] or NULL. */
+int hipac_resnet18_forward(const void* d_packed, int num_classes,
+                           const void* d_batch, int layout, int n_patches,
+                           float* d_feats, float* d_logits,
+                           void* d_workspace, size_t workspace_bytes, int chunk, void* stream);
+
+/* Test hook: one conv layer of the network on its own (layer index 0..19, network order), bf16 NHWC in/out
+ * (layer 0 takes the S2D16 batch), optional residual.  Used by the per-layer parity tests. */
+int hipac_resnet18_conv_layer(const void* d_packed, int num_classes, int layer,
+                              const void* d_in, const void* d_residual, void* d_out,
+                              int n_patches, int relu, void* stream);
+
+/* Number of kernel launches issued by this library on the calling thread since the last reset
+ * (bench.py's "gpu_launches"). */
+long long hipac_launch_count(int reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HIPAC_B200_H */

@@ -1,0 +1,129 @@
+"""ctypes binding of libhipac_b200.so (the C ABI in include/hipac_b200.h).
+
+The shared library is built in-tree by ``build()`` (nvcc, sm_100a only) and loaded lazily.
+There is no CPU or PyTorch fallback: if the library is missing, ``lib()`` raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_CSRC = os.path.join(_HERE, "csrc")
+LIB_PATH = os.path.join(_HERE, "libhipac_b200.so")
+SOURCES = ["capi.cu", "tile_scan.cu", "tile_scan_fused.cu", "resnet18.cu"]
+HEADER = os.path.join(os.path.dirname(_HERE), "include", "hipac_b200.h")
+
+LAYOUT_NHWC3_BF16 = 1
+LAYOUT_S2D16_BF16 = 2
+SCAN_AUTO, SCAN_DIRECT, SCAN_FUSED = 0, 1, 2
+RESNET18_NUM_CONVS = 20
+
+_lock = threading.Lock()
+_lib = None
+
+
+def _nvcc() -> str:
+    for cand in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", "nvcc"):
+        if cand and (os.path.isabs(cand) and os.path.exists(cand) or not os.path.isabs(cand)):
+            return cand
+    return "nvcc"
+
+
+def _stale() -> bool:
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    deps = [os.path.join(_CSRC, f) for f in os.listdir(_CSRC)] + [HEADER]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile every CUDA source for sm_100a into ``libhipac_b200.so`` (in-tree)."""
+    if not force and not _stale():
+        return LIB_PATH
+    objs = []
+    build_dir = os.path.join(_HERE, "build")
+    os.makedirs(build_dir, exist_ok=True)
+    flags = ["-std=c++17", "-O3", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a",
+             "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
+    procs = []
+    for src in SOURCES:
+        obj = os.path.join(build_dir, src.replace(".cu", ".o"))
+        cmd = [_nvcc(), *flags, "-c", os.path.join(_CSRC, src), "-o", obj]
+        if verbose:
+            cmd.insert(1, "-Xptxas=-v")
+            print(" ".join(cmd))
+        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        objs.append(obj)
+    for src, pr in procs:
+        out, _ = pr.communicate()
+        if verbose and out:
+            print(out)
+        if pr.returncode != 0:
+            raise RuntimeError(f"nvcc failed for {src}:\n{out}")
+    cmd = [_nvcc(), "-shared", "-o", LIB_PATH + ".tmp", *objs, "-gencode", "arch=compute_100a,code=sm_100a"]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"link failed:\n{r.stdout}")
+    os.replace(LIB_PATH + ".tmp", LIB_PATH)
+    return LIB_PATH
+
+
+def _declare(l):
+    vp, i32, i64, sz = C.c_void_p, C.c_int, C.c_int64, C.c_size_t
+    l.hipac_last_error.restype = C.c_char_p
+    l.hipac_last_error.argtypes = []
+    l.hipac_abi_version.restype = i32
+    l.hipac_abi_version.argtypes = []
+    l.hipac_launch_count.restype = C.c_longlong
+    l.hipac_launch_count.argtypes = [i32]
+    l.hipac_tile_scan_workspace_bytes.restype = sz
+    l.hipac_tile_scan_workspace_bytes.argtypes = [i32] * 7
+    l.hipac_tile_scan.restype = i32
+    l.hipac_tile_scan.argtypes = [vp, i32, i32, i64, vp, i64, i32, i32, i32, i32, vp, vp, vp, vp, i32, vp, i32,
+                                  vp, sz, i32, vp]
+    l.hipac_pillow_coeffs.restype = i32
+    l.hipac_pillow_coeffs.argtypes = [i32, vp, vp, vp]
+    l.hipac_normalize_lut_bf16.restype = i32
+    l.hipac_normalize_lut_bf16.argtypes = [vp]
+    l.hipac_resnet18_packed_bytes.restype = sz
+    l.hipac_resnet18_packed_bytes.argtypes = [i32]
+    l.hipac_resnet18_pack.restype = i32
+    l.hipac_resnet18_pack.argtypes = [C.POINTER(vp), i32, i32, C.c_float, vp, sz]
+    l.hipac_resnet18_workspace_bytes.restype = sz
+    l.hipac_resnet18_workspace_bytes.argtypes = [i32, i32]
+    l.hipac_resnet18_forward.restype = i32
+    l.hipac_resnet18_forward.argtypes = [vp, i32, vp, i32, i32, vp, vp, vp, sz, i32, vp]
+    l.hipac_resnet18_conv_layer.restype = i32
+    l.hipac_resnet18_conv_layer.argtypes = [vp, i32, i32, vp, vp, vp, i32, i32, vp]
+
+
+EXPORTS = [
+    "hipac_last_error", "hipac_abi_version", "hipac_launch_count", "hipac_tile_scan_workspace_bytes",
+    "hipac_tile_scan", "hipac_pillow_coeffs", "hipac_normalize_lut_bf16", "hipac_resnet18_packed_bytes",
+    "hipac_resnet18_pack", "hipac_resnet18_workspace_bytes", "hipac_resnet18_forward",
+    "hipac_resnet18_conv_layer",
+]
+
+
+def lib():
+    """The loaded shared library; raises if it has not been built (no fallback path exists)."""
+    global _lib
+    with _lock:
+        if _lib is None:
+            if not os.path.exists(LIB_PATH):
+                raise RuntimeError(
+                    f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                    "(the HiPAC B200 path has no CPU/PyTorch fallback)")
+            l = C.CDLL(LIB_PATH)
+            _declare(l)
+            _lib = l
+    return _lib
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        raise RuntimeError(f"{what} failed ({rc}): {lib().hipac_last_error().decode()}")

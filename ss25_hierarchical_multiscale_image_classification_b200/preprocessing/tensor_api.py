@@ -1,0 +1,114 @@
+"""In-HBM patch extraction: the fast path under the reference's ``extract_patches``.
+
+``extract_patches_tensor`` replaces the hot loop of the reference's ``extract_patches``
+(``src/main.py:682-727``) and the ``Resize/ToTensor/Normalize`` of its feature-extraction
+transform (``src/main.py:812-818``) for one level image already resident in device memory.
+All arithmetic happens in ``libhipac_b200.so`` (``hipac_tile_scan``); this module only sizes
+buffers and moves pointers.  There is no CPU fallback.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import torch
+
+from .. import _lib
+
+PATCH_SIZES = {0: 1792, 1: 896, 2: 448, 3: 224}   # reference src/main.py:614
+OUT = 224
+
+_LAYOUTS = {"nhwc3": _lib.LAYOUT_NHWC3_BF16, "s2d16": _lib.LAYOUT_S2D16_BF16}
+_MODES = {"auto": _lib.SCAN_AUTO, "direct": _lib.SCAN_DIRECT, "fused": _lib.SCAN_FUSED}
+
+
+def patch_and_stride(level: int, stride=None, patch_size: int = 224):
+    """``stride = stride or patch_size`` happens BEFORE the level map overwrites the patch size
+    (reference ``src/main.py:611`` vs ``614-615``), so the CLI stride is 224 at every level."""
+    s = stride or patch_size
+    return PATCH_SIZES.get(level, 224), int(s)
+
+
+def grid_shape(width: int, height: int, stride: int):
+    """(nx, ny) of the candidate grid ``range(0,W,S) x range(0,H,S)`` (reference ``src/main.py:682-686``)."""
+    return (width + stride - 1) // stride, (height + stride - 1) // stride
+
+
+@dataclass
+class PatchBatch:
+    """Survivors of one ``hipac_tile_scan`` call, in the reference's emission order (x outer, y inner)."""
+    coords: torch.Tensor            # int32 [N,2] (x, y) in level pixels
+    labels: torch.Tensor            # uint8 [N] 1 = tumor, 0 = normal
+    batch: torch.Tensor | None      # bf16 [N,224,224,3] ("nhwc3") or [N,112,112,16] ("s2d16")
+    images_u8: torch.Tensor | None  # uint8 [N,224,224,3] Pillow-exact resized patches
+    layout: str | None
+    candidates: int
+    patch: int
+    stride: int
+    level: int
+
+    def __len__(self):
+        return int(self.coords.shape[0])
+
+
+def batch_shape(n: int, layout: str):
+    return (n, OUT, OUT, 3) if layout == "nhwc3" else (n, OUT // 2, OUT // 2, 16)
+
+
+def extract_patches_tensor(level_img: torch.Tensor, lesion_mask: torch.Tensor | None, level: int,
+                           stride=None, row_range=None, patch_size: int = 224, layout: str | None = "s2d16",
+                           want_u8: bool = False, mode: str = "auto", capacity: int | None = None,
+                           stream: torch.cuda.Stream | None = None) -> PatchBatch:
+    """Tile one level image (uint8 ``[H,W,3]`` on a CUDA device) exactly as the reference does.
+
+    ``lesion_mask``: uint8 ``[H,W]`` (>0 = lesion, the rasterised ``parse_xml_mask`` output,
+    reference ``src/main.py:372-410``) or ``None`` -> every patch "normal" (``src/main.py:714-716``).
+    ``row_range=(i0,i1)`` restricts to candidate grid rows ``y//stride in [i0,i1)`` -- the
+    multi-GPU shard unit.  Synchronises once to read the survivor count.
+    """
+    l = _lib.lib()
+    if not (level_img.is_cuda and level_img.dtype == torch.uint8 and level_img.dim() == 3 and level_img.shape[2] == 3):
+        raise ValueError("level_img must be a CUDA uint8 tensor of shape [H, W, 3]")
+    if level_img.stride(2) != 1 or level_img.stride(1) != 3:
+        level_img = level_img.contiguous()
+    H, W = int(level_img.shape[0]), int(level_img.shape[1])
+    pitch = int(level_img.stride(0))
+    if lesion_mask is not None:
+        if not (lesion_mask.is_cuda and lesion_mask.dtype == torch.uint8 and tuple(lesion_mask.shape) == (H, W)):
+            raise ValueError("lesion_mask must be a CUDA uint8 tensor of shape [H, W]")
+        if lesion_mask.stride(1) != 1:
+            lesion_mask = lesion_mask.contiguous()
+    P, S = patch_and_stride(level, stride, patch_size)
+    nx, ny_all = grid_shape(W, H, S)
+    i0, i1 = (0, ny_all) if row_range is None else (int(row_range[0]), int(row_range[1]))
+    if not (0 <= i0 <= i1 <= ny_all):
+        raise ValueError(f"row_range {row_range} outside the candidate grid rows [0, {ny_all}]")
+    n_cand = nx * (i1 - i0)
+    cap = n_cand if capacity is None else int(capacity)
+    dev = level_img.device
+    st = stream or torch.cuda.current_stream(dev)
+    with torch.cuda.device(dev), torch.cuda.stream(st):
+        coords = torch.empty((max(cap, 1), 2), dtype=torch.int32, device=dev)
+        labels = torch.empty((max(cap, 1),), dtype=torch.uint8, device=dev)
+        count = torch.zeros((2,), dtype=torch.int32, device=dev)
+        batch = torch.empty(batch_shape(max(cap, 1), layout), dtype=torch.bfloat16, device=dev) if layout else None
+        u8 = torch.empty((max(cap, 1), OUT, OUT, 3), dtype=torch.uint8, device=dev) if want_u8 else None
+        m = _MODES[mode]
+        ws_bytes = l.hipac_tile_scan_workspace_bytes(H, W, P, S, i0, i1, m)
+        if ws_bytes == 0:
+            raise RuntimeError("hipac_tile_scan_workspace_bytes: " + l.hipac_last_error().decode())
+        ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+        rc = l.hipac_tile_scan(
+            level_img.data_ptr(), H, W, pitch,
+            lesion_mask.data_ptr() if lesion_mask is not None else None,
+            int(lesion_mask.stride(0)) if lesion_mask is not None else 0,
+            P, S, i0, i1, coords.data_ptr(), labels.data_ptr(),
+            u8.data_ptr() if u8 is not None else None,
+            batch.data_ptr() if batch is not None else None, _LAYOUTS[layout] if layout else 0,
+            count.data_ptr(), cap, ws.data_ptr(), ws_bytes, m, st.cuda_stream)
+        _lib.check(rc, "hipac_tile_scan")
+        n, n_c = (int(v) for v in count.cpu())
+    if n > cap:
+        raise RuntimeError(f"{n} survivors exceed capacity {cap}; pass a smaller row_range or a larger capacity")
+    return PatchBatch(coords=coords[:n], labels=labels[:n], batch=batch[:n] if batch is not None else None,
+                      images_u8=u8[:n] if u8 is not None else None, layout=layout, candidates=n_c, patch=P,
+                      stride=S, level=level)

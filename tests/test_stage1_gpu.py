@@ -1,0 +1,113 @@
+"""Stage-1 parity on the GPU: hipac_tile_scan (through the C ABI) vs the CPU oracle and the
+golden vectors frozen from the real reference.  Everything here is bit exact."""
+import zlib
+
+import numpy as np
+import pytest
+
+from conftest import golden_stage1_cases, load_golden, slide_for
+from oracle import hipac_oracle as orc
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+
+def _run(level_img, mask, level, stride, mode="auto", layout="nhwc3", row_range=None):
+    from ss25_hierarchical_multiscale_image_classification_b200.preprocessing import extract_patches_tensor
+    img = torch.from_numpy(level_img).cuda()
+    m = torch.from_numpy(mask).cuda() if mask is not None else None
+    return extract_patches_tensor(img, m, level, stride=stride, layout=layout, want_u8=True, mode=mode,
+                                  row_range=row_range)
+
+
+def _bf16_bits(t):
+    return t.view(torch.int16).cpu().numpy().view(np.uint16)
+
+
+MODES = ["direct", "auto"]
+
+
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("case", golden_stage1_cases())
+def test_golden_reference_vectors(case, mode):
+    g = load_golden(f"stage1_{case}.npz")
+    slide = slide_for(g)
+    level = int(g["level"])
+    stride = None if int(g["stride"]) < 0 else int(g["stride"])
+    out = _run(slide.level_array(level), slide.lesion_mask(level), level, stride, mode=mode)
+    assert np.array_equal(out.coords.cpu().numpy(), g["coords"])
+    assert np.array_equal(out.labels.cpu().numpy(), g["labels"])
+    u8 = out.images_u8.cpu().numpy()
+    crc = np.array([zlib.crc32(im.tobytes()) for im in u8], dtype=np.uint32)
+    assert np.array_equal(crc, g["crc32"])
+    # normalised bf16 batch == bf16(ToTensor+Normalize) of the exact uint8 image
+    want = orc.to_bf16_bits(orc.normalize_u8(u8)) if len(u8) else np.zeros((0, 224, 224, 3), np.uint16)
+    assert np.array_equal(_bf16_bits(out.batch), want)
+
+
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("level,stride,w,h", [(3, None, 1117, 903), (2, None, 1500, 1100), (2, 448, 1500, 1100),
+                                               (1, None, 2100, 1900), (1, 896, 2100, 1900), (0, None, 2500, 2300),
+                                               (0, 1792, 4000, 3700), (1, 333, 2100, 1900), (3, 100, 700, 500),
+                                               (3, None, 100, 90), (2, None, 449, 225)])
+def test_random_images_vs_oracle(level, stride, w, h, mode):
+    rng = np.random.default_rng(level * 1000 + w)
+    img = rng.integers(200, 256, size=(h, w, 3), dtype=np.uint8)          # hovers around the 240 threshold
+    img[h // 5: h // 2, w // 6: w // 2] = rng.integers(0, 256, size=(h // 2 - h // 5, w // 2 - w // 6, 3), dtype=np.uint8)
+    mask = np.zeros((h, w), np.uint8)
+    mask[h // 4: h // 4 + 37, w // 3: w // 3 + 55] = 255
+    mask[h - 1, w - 1] = 1                                                 # last pixel, value 1 (>0 counts)
+    want = orc.extract_patches_oracle(img, mask, level, stride=stride)
+    out = _run(img, mask, level, stride, mode=mode)
+    assert out.candidates == want["candidates"]
+    assert np.array_equal(out.coords.cpu().numpy(), want["coords"])
+    assert np.array_equal(out.labels.cpu().numpy(), want["labels"])
+    assert np.array_equal(out.images_u8.cpu().numpy(), want["images"])
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_s2d16_layout_is_a_permutation_of_nhwc3(mode):
+    rng = np.random.default_rng(7)
+    img = rng.integers(0, 256, size=(700, 900, 3), dtype=np.uint8)
+    a = _run(img, None, 2, None, mode=mode, layout="nhwc3")
+    b = _run(img, None, 2, None, mode=mode, layout="s2d16")
+    assert len(a) == len(b) > 0
+    x = a.batch.view(torch.int16).reshape(len(a), 112, 2, 112, 2, 3).permute(0, 1, 3, 2, 4, 5).reshape(len(a), 112, 112, 12)
+    y = b.batch.view(torch.int16)
+    assert torch.equal(y[..., :12], x)
+    assert int(y[..., 12:].abs().max()) == 0
+    assert int(a.labels.sum()) == 0                                        # no mask -> all "normal"
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_row_range_shards_concatenate_to_full(mode):
+    rng = np.random.default_rng(3)
+    img = rng.integers(100, 256, size=(1300, 1000, 3), dtype=np.uint8)
+    full = _run(img, None, 2, None, mode=mode)
+    ny = (1300 + 223) // 224
+    parts = [_run(img, None, 2, None, mode=mode, row_range=r) for r in [(0, 2), (2, 2), (2, 5), (5, ny)]]
+    coords = torch.cat([p.coords for p in parts]).cpu().numpy()
+    imgs = torch.cat([p.images_u8 for p in parts]).cpu().numpy()
+    order = np.lexsort((coords[:, 1], coords[:, 0]))                       # canonical (x, y) order
+    assert np.array_equal(coords[order], full.coords.cpu().numpy())
+    assert np.array_equal(imgs[order], full.images_u8.cpu().numpy())
+    assert sum(p.candidates for p in parts) == full.candidates
+
+
+def test_pitched_input_and_errors():
+    from ss25_hierarchical_multiscale_image_classification_b200.preprocessing import extract_patches_tensor
+    rng = np.random.default_rng(5)
+    img = rng.integers(0, 256, size=(500, 611, 3), dtype=np.uint8)
+    big = torch.zeros((500, 640, 3), dtype=torch.uint8, device="cuda")
+    big[:, :611] = torch.from_numpy(img).cuda()
+    view = big[:, :611]                                                    # row pitch 1920 bytes, W = 611
+    out = extract_patches_tensor(view, None, 3, want_u8=True, layout=None)
+    want = orc.extract_patches_oracle(img, None, 3)
+    assert np.array_equal(out.coords.cpu().numpy(), want["coords"])
+    assert np.array_equal(out.images_u8.cpu().numpy(), want["images"])
+    with pytest.raises(ValueError):
+        extract_patches_tensor(view.float(), None, 3)
+    with pytest.raises(ValueError):
+        extract_patches_tensor(view, None, 3, row_range=(0, 99))
+    with pytest.raises(RuntimeError):
+        extract_patches_tensor(view, None, 3, capacity=1)
