@@ -1,8 +1,558 @@
-// Stage 2 (ResNet18 forward) -- placeholder until the tcgen05 kernels land.
+// Stage 2 of the HiPAC hot path: ResNet18 forward (reference src/models/resnet.py:22-77, i.e. the
+// torchvision resnet18 trunk in eval mode + global average pool [+ Linear(512,k)]) as implicit-GEMM
+// tcgen05/TMEM kernels.  Activations are bf16 NHWC; eval-mode BatchNorm is folded into the weights
+// (fp32 fold, bf16 round) and a per-channel fp32 bias added in the epilogue together with the
+// residual and ReLU.  The A operand (im2col of the activations) is produced by TMA im2col loads,
+// the B operand (weights, K-major) by tiled TMA loads; accumulators live in TMEM, double buffered
+// so the epilogue of tile i overlaps the MMAs of tile i+1.  See DESIGN.md.
+#include <cuda.h>
+
+#include <cmath>
+#include <cstring>
+#include <vector>
+
 #include "common.cuh"
+#include "resnet18_layers.h"
+#include "umma.cuh"
+
+namespace hipac {
+
+// ==========================================================================================
+// implicit-GEMM convolution kernel
+// ==========================================================================================
+struct ConvParams {
+  int M_total;       // images * hout * wout (GEMM M)
+  int hw_out, wout;  // hout*wout, wout
+  int stride, pad;
+  int kw;            // filter width (taps per filter row)
+  int kc_blocks;     // 64-channel blocks per tap (cin / 64)
+  int num_kb;        // k-blocks per tile
+  int num_m_tiles, num_n_tiles;
+  int cout;
+  int relu;
+  const float* bias;
+  const __nv_bfloat16* residual;
+  __nv_bfloat16* out;
+};
+
+constexpr int kBM = 128;
+constexpr int kABytes = kBM * 128;  // 128 rows x 64 bf16 (or 4 taps x 128 rows x 16 bf16 for conv1)
+constexpr int kConvThreads = 192;   // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
+
+template <int BN>
+struct ConvCfg {
+  static constexpr int kBBytes = BN * 128;
+  static constexpr int kStage = kABytes + kBBytes;
+  static constexpr int kStages = 6;
+  static constexpr int kTmemCols = 2 * BN;
+  static constexpr int kSmemBytes = kStages * kStage + 1024 /*alignment slack*/ + 256 /*barriers*/;
+};
+
+template <int BN, bool CONV1>
+__global__ void __launch_bounds__(kConvThreads, 1)
+k_conv_umma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvParams p) {
+  using Cfg = ConvCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full = reinterpret_cast<uint64_t*>(base + Cfg::kStages * Cfg::kStage);
+  uint64_t* empty = full + Cfg::kStages;
+  uint64_t* tfull = empty + Cfg::kStages;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    ptx::prefetch_tensormap(&tmA);
+    ptx::prefetch_tensormap(&tmB);
+    for (int s = 0; s < Cfg::kStages; s++) ptx::mbar_init(&full[s], 1), ptx::mbar_init(&empty[s], 1);
+    for (int a = 0; a < 2; a++) ptx::mbar_init(&tfull[a], 1), ptx::mbar_init(&tempty[a], 4);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_slot, Cfg::kTmemCols);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_tile = tile / p.num_n_tiles, n_tile = tile - m_tile * p.num_n_tiles;
+        const int m0 = m_tile * kBM;
+        const int img = m0 / p.hw_out, rem = m0 - img * p.hw_out;
+        const int p0 = rem / p.wout, q0 = rem - p0 * p.wout;
+        const int cw = q0 * p.stride - p.pad, ch = p0 * p.stride - p.pad;
+        for (int kb = 0; kb < p.num_kb; kb++) {
+          ptx::mbar_wait(&empty[stage], phase ^ 1);
+          ptx::mbar_arrive_expect_tx(&full[stage], Cfg::kStage);
+          uint8_t* a_dst = base + stage * Cfg::kStage;
+          uint8_t* b_dst = a_dst + kABytes;
+          if (CONV1) {
+            // k-block = one row `a` of the 4x4 space-to-depth filter: 4 taps of 16 channels each
+            for (int b = 0; b < 4; b++)
+              ptx::tma_load_im2col_4d(a_dst + b * 4096, &tmA, &full[stage], 0, cw, ch, img, (uint16_t)b, (uint16_t)kb);
+          } else {
+            const int tap = kb / p.kc_blocks, kc = kb - tap * p.kc_blocks;
+            const int r = tap / p.kw, s = tap - r * p.kw;
+            ptx::tma_load_im2col_4d(a_dst, &tmA, &full[stage], kc * 64, cw, ch, img, (uint16_t)s, (uint16_t)r);
+          }
+          ptx::tma_load_2d(b_dst, &tmB, &full[stage], kb * 64, n_tile * BN);
+          if (++stage == Cfg::kStages) stage = 0, phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (one thread) =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = ptx::make_idesc_bf16(kBM, BN);
+      int stage = 0;
+      uint32_t phase = 0, acc = 0, acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        ptx::mbar_wait(&tempty[acc], acc_phase ^ 1);  // epilogue has drained this accumulator
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < p.num_kb; kb++) {
+          ptx::mbar_wait(&full[stage], phase);
+          ptx::tc_fence_after();
+          const uint32_t a_addr = ptx::smem_u32(base + stage * Cfg::kStage);
+          const uint32_t b_addr = a_addr + kABytes;
+#pragma unroll
+          for (int k = 0; k < 4; k++) {  // 4 x (K = 16) per 64-wide k-block
+            const uint64_t adesc = CONV1 ? ptx::make_smem_desc(a_addr + k * 4096, 32) : ptx::make_smem_desc(a_addr + k * 32, 128);
+            const uint64_t bdesc = ptx::make_smem_desc(b_addr + k * 32, 128);
+            ptx::umma_bf16(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          ptx::umma_commit(&empty[stage]);  // smem slot reusable once these MMAs retire
+          if (++stage == Cfg::kStages) stage = 0, phase ^= 1;
+        }
+        ptx::umma_commit(&tfull[acc]);  // accumulator complete -> epilogue
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else {
+    // ===================== epilogue: TMEM -> +bias (+residual) -> ReLU -> bf16 NHWC =====================
+    const int wq = warp & 3;  // TMEM lane quarter this warp may access
+    const int row = wq * 32 + lane;
+    uint32_t acc = 0, acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_tile = tile / p.num_n_tiles, n_tile = tile - m_tile * p.num_n_tiles;
+      const int m = m_tile * kBM + row;
+      const bool valid = m < p.M_total;
+      ptx::mbar_wait(&tfull[acc], acc_phase);
+      ptx::tc_fence_after();
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t v[32];
+        ptx::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(wq * 32) << 16) + acc * BN + c0, v);
+        ptx::tmem_ld_wait();
+        if (valid) {
+          const int n0 = n_tile * BN + c0;
+          const size_t off = (size_t)m * p.cout + n0;
+          const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0);
+          uint4 res[4];
+          if (p.residual) {
+            const uint4* r4 = reinterpret_cast<const uint4*>(p.residual + off);
+#pragma unroll
+            for (int i = 0; i < 4; i++) res[i] = __ldg(r4 + i);
+          }
+          uint4 o[4];
+#pragma unroll
+          for (int i = 0; i < 8; i++) {
+            const float4 b = __ldg(b4 + i);
+            float x0 = __uint_as_float(v[4 * i + 0]) + b.x, x1 = __uint_as_float(v[4 * i + 1]) + b.y;
+            float x2 = __uint_as_float(v[4 * i + 2]) + b.z, x3 = __uint_as_float(v[4 * i + 3]) + b.w;
+            if (p.residual) {
+              const uint32_t* rw = reinterpret_cast<const uint32_t*>(&res[i >> 1]) + (i & 1) * 2;
+              const __nv_bfloat162 ra = *reinterpret_cast<const __nv_bfloat162*>(&rw[0]);
+              const __nv_bfloat162 rb = *reinterpret_cast<const __nv_bfloat162*>(&rw[1]);
+              x0 += __bfloat162float(ra.x), x1 += __bfloat162float(ra.y);
+              x2 += __bfloat162float(rb.x), x3 += __bfloat162float(rb.y);
+            }
+            if (p.relu) x0 = fmaxf(x0, 0.f), x1 = fmaxf(x1, 0.f), x2 = fmaxf(x2, 0.f), x3 = fmaxf(x3, 0.f);
+            __nv_bfloat162 lo = __floats2bfloat162_rn(x0, x1), hi = __floats2bfloat162_rn(x2, x3);
+            uint32_t* ow = reinterpret_cast<uint32_t*>(&o[i >> 1]) + (i & 1) * 2;
+            ow[0] = *reinterpret_cast<uint32_t*>(&lo);
+            ow[1] = *reinterpret_cast<uint32_t*>(&hi);
+          }
+          uint4* dst = reinterpret_cast<uint4*>(p.out + off);
+#pragma unroll
+          for (int i = 0; i < 4; i++) dst[i] = o[i];
+        }
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&tempty[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc(tmem_base, Cfg::kTmemCols);
+}
+
+// ==========================================================================================
+// small memory-bound kernels
+// ==========================================================================================
+// MaxPool 3x3 / stride 2 / pad 1 on bf16 NHWC [n,112,112,64] -> [n,56,56,64]; 8 channels per thread.
+__global__ void __launch_bounds__(256) k_maxpool(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out,
+                                                 int n_img) {
+  const int64_t total = (int64_t)n_img * 56 * 56 * 8;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int cg = (int)(t & 7);
+    int64_t pix = t >> 3;
+    const int ox = (int)(pix % 56);
+    pix /= 56;
+    const int oy = (int)(pix % 56);
+    const int img = (int)(pix / 56);
+    __nv_bfloat162 m[4];
+    bool first = true;
+#pragma unroll
+    for (int dy = -1; dy <= 1; dy++) {
+      const int iy = 2 * oy + dy;
+      if (iy < 0 || iy >= 112) continue;
+#pragma unroll
+      for (int dx = -1; dx <= 1; dx++) {
+        const int ix = 2 * ox + dx;
+        if (ix < 0 || ix >= 112) continue;
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(in + (((int64_t)img * 112 + iy) * 112 + ix) * 64 + cg * 8));
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+        if (first) {
+          m[0] = h[0], m[1] = h[1], m[2] = h[2], m[3] = h[3];
+          first = false;
+        } else {
+          m[0] = __hmax2(m[0], h[0]), m[1] = __hmax2(m[1], h[1]), m[2] = __hmax2(m[2], h[2]), m[3] = __hmax2(m[3], h[3]);
+        }
+      }
+    }
+    *reinterpret_cast<uint4*>(out + (((int64_t)img * 56 + oy) * 56 + ox) * 64 + cg * 8) = *reinterpret_cast<uint4*>(m);
+  }
+}
+
+// Global average pool over 7x7 (fp32 accumulate) + optional Linear(512,k) in fp32. One CTA per patch.
+__global__ void __launch_bounds__(256) k_avgpool_fc(const __nv_bfloat16* __restrict__ in, float* __restrict__ feats,
+                                                    float* __restrict__ logits, const float* __restrict__ fc_w,
+                                                    const float* __restrict__ fc_b, int num_classes) {
+  const int img = blockIdx.x;
+  __shared__ float f[512];
+  const __nv_bfloat16* src = in + (int64_t)img * 49 * 512;
+  for (int c2 = threadIdx.x; c2 < 256; c2 += 256) {
+    float s0 = 0.f, s1 = 0.f;
+    for (int px = 0; px < 49; px++) {
+      const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(src + px * 512 + 2 * c2);
+      s0 += __bfloat162float(v.x), s1 += __bfloat162float(v.y);
+    }
+    s0 *= (1.0f / 49.0f), s1 *= (1.0f / 49.0f);
+    f[2 * c2] = s0, f[2 * c2 + 1] = s1;
+    feats[(int64_t)img * 512 + 2 * c2] = s0;
+    feats[(int64_t)img * 512 + 2 * c2 + 1] = s1;
+  }
+  if (!logits) return;
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int k = warp; k < num_classes; k += 8) {
+    float s = 0.f;
+    for (int c = lane; c < 512; c += 32) s += f[c] * __ldg(fc_w + k * 512 + c);
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) logits[(int64_t)img * num_classes + k] = s + __ldg(fc_b + k);
+  }
+}
+
+// bf16 NHWC3 [n,224,224,3] -> S2D16 [n,112,112,16] (used when the caller hands the plain layout).
+__global__ void __launch_bounds__(256) k_pack_s2d16(const uint16_t* __restrict__ in, uint16_t* __restrict__ out, int n_img) {
+  const int64_t total = (int64_t)n_img * 112 * 112;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int X = (int)(t % 112);
+    const int Y = (int)((t / 112) % 112);
+    const int64_t img = t / (112 * 112);
+    uint16_t v[16];
+#pragma unroll
+    for (int dy = 0; dy < 2; dy++)
+#pragma unroll
+      for (int dx = 0; dx < 2; dx++)
+#pragma unroll
+        for (int c = 0; c < 3; c++) v[(dy * 2 + dx) * 3 + c] = in[((img * 224 + 2 * Y + dy) * 224 + 2 * X + dx) * 3 + c];
+    v[12] = v[13] = v[14] = v[15] = 0;
+    uint4* dst = reinterpret_cast<uint4*>(out + t * 16);
+    dst[0] = *reinterpret_cast<uint4*>(&v[0]);
+    dst[1] = *reinterpret_cast<uint4*>(&v[8]);
+  }
+}
+
+// ==========================================================================================
+// host: tensor maps, launches
+// ==========================================================================================
+typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                   const int*, const int*, cuuint32_t, cuuint32_t, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeIm2colFn g_encode_im2col = nullptr;
+static EncodeTiledFn g_encode_tiled = nullptr;
+static int g_num_sms = 0;
+
+static int init_driver_api() {
+  if (g_encode_im2col && g_encode_tiled && g_num_sms) return 0;
+  cudaDriverEntryPointQueryResult q;
+  void* fn = nullptr;
+  HIPAC_CHECK_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &fn, cudaEnableDefault, &q));
+  HIPAC_REQUIRE(fn && q == cudaDriverEntryPointSuccess, "driver lacks cuTensorMapEncodeIm2col");
+  g_encode_im2col = (EncodeIm2colFn)fn;
+  HIPAC_CHECK_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+  HIPAC_REQUIRE(fn && q == cudaDriverEntryPointSuccess, "driver lacks cuTensorMapEncodeTiled");
+  g_encode_tiled = (EncodeTiledFn)fn;
+  int dev = 0;
+  HIPAC_CHECK_CUDA(cudaGetDevice(&dev));
+  HIPAC_CHECK_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+  return 0;
+}
+
+// NHWC activation tensor [n][h][w][c] (bf16) as an im2col map: box = 128 output pixels x `chan_box` channels.
+static int make_im2col_map(CUtensorMap* map, const void* ptr, int n, int h, int w, int c, int chan_box, int ksize, int stride,
+                           int pad_lo, int pad_hi, CUtensorMapSwizzle swz) {
+  cuuint64_t dims[4] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
+  cuuint64_t strides[3] = {(cuuint64_t)c * 2, (cuuint64_t)w * c * 2, (cuuint64_t)h * w * c * 2};
+  int lower[2] = {-pad_lo, -pad_lo};
+  int upper[2] = {pad_hi - (ksize - 1), pad_hi - (ksize - 1)};
+  cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
+  CUresult r = g_encode_im2col(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, lower, upper,
+                               (cuuint32_t)chan_box, (cuuint32_t)kBM, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+                               CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeIm2col failed with CUresult " + std::to_string((int)r));
+    return -5;
+  }
+  // Same driver quirk CUTLASS works around (copy_traits_sm90_im2col.hpp): for tensors smaller than 128 KiB
+  // drivers <= 13.1 set a descriptor bit that breaks im2col loads.
+  int drv = 0;
+  cudaDriverGetVersion(&drv);
+  if (drv <= 13010 && (size_t)n * h * w * c * 2 < 131072) reinterpret_cast<uint64_t*>(map)[1] &= ~(1ull << 21);
+  return 0;
+}
+
+// Weights [cout][K] bf16, K-major: box = 64 (K) x bn rows, 128-byte swizzle.
+static int make_weight_map(CUtensorMap* map, const void* ptr, int cout, int K, int bn) {
+  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)cout};
+  cuuint64_t strides[1] = {(cuuint64_t)K * 2};
+  cuuint32_t box[2] = {64, (cuuint32_t)bn};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode_tiled(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
+    return -5;
+  }
+  return 0;
+}
+
+template <int BN, bool CONV1>
+static int launch_conv_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvParams& p, cudaStream_t stream) {
+  using Cfg = ConvCfg<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    HIPAC_CHECK_CUDA(cudaFuncSetAttribute(k_conv_umma<BN, CONV1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  const int tiles = p.num_m_tiles * p.num_n_tiles;
+  const int grid = tiles < g_num_sms ? tiles : g_num_sms;
+  k_conv_umma<BN, CONV1><<<grid, kConvThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, p);
+  count_launch(1);
+  HIPAC_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// One conv layer of the network on `n` patches. in/out are bf16 NHWC (layer 0: S2D16 input).
+static int run_conv(const uint8_t* d_packed, const PackedLayout& L, int layer, const void* in, const void* residual, void* out,
+                    int n, bool relu, cudaStream_t stream) {
+  const ConvSpec& cs = kConvs[layer];
+  const int K = conv_gemm_k(layer);
+  ConvParams p;
+  p.M_total = n * cs.hout * cs.hout;
+  p.hw_out = cs.hout * cs.hout, p.wout = cs.hout;
+  p.cout = cs.cout;
+  p.relu = relu ? 1 : 0;
+  p.bias = reinterpret_cast<const float*>(d_packed + L.b_off[layer]);
+  p.residual = reinterpret_cast<const __nv_bfloat16*>(residual);
+  p.out = reinterpret_cast<__nv_bfloat16*>(out);
+  p.num_m_tiles = (p.M_total + kBM - 1) / kBM;
+  const int bn = cs.cout >= 128 ? 128 : 64;
+  p.num_n_tiles = cs.cout / bn;
+  CUtensorMap tmA, tmB;
+  if (int e = make_weight_map(&tmB, d_packed + L.w_off[layer], cs.cout, K, bn)) return e;
+  if (layer == 0) {
+    // 7x7/s2/p3 over 3 channels == 4x4/s1 over the 2x2 space-to-depth image (16 ch), pad 2 before / 1 after
+    p.stride = 1, p.pad = 2, p.kw = 4, p.kc_blocks = 1, p.num_kb = 4;
+    if (int e = make_im2col_map(&tmA, in, n, 112, 112, 16, 16, 4, 1, 2, 1, CU_TENSOR_MAP_SWIZZLE_32B)) return e;
+    return launch_conv_t<64, true>(tmA, tmB, p, stream);
+  }
+  p.stride = cs.stride, p.pad = cs.pad, p.kw = cs.k, p.kc_blocks = cs.cin / 64, p.num_kb = cs.k * cs.k * p.kc_blocks;
+  if (int e = make_im2col_map(&tmA, in, n, cs.hin, cs.hin, cs.cin, 64, cs.k, cs.stride, cs.pad, cs.pad, CU_TENSOR_MAP_SWIZZLE_128B))
+    return e;
+  return bn == 128 ? launch_conv_t<128, false>(tmA, tmB, p, stream) : launch_conv_t<64, false>(tmA, tmB, p, stream);
+}
+
+static uint16_t host_bf16(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7F800000u) == 0x7F800000u) return (uint16_t)(u >> 16);  // inf / nan passthrough
+  u += 0x7FFFu + ((u >> 16) & 1u);
+  return (uint16_t)(u >> 16);
+}
+
+// per-chunk activation buffers (bf16 NHWC), sizes per patch
+constexpr size_t kC1Bytes = (size_t)112 * 112 * 64 * 2;  // conv1 output
+constexpr size_t kActBytes = (size_t)56 * 56 * 64 * 2;   // largest post-pool activation
+constexpr size_t kS2dBytes = (size_t)112 * 112 * 16 * 2;
+
+static int clamp_chunk(int chunk, int n) {
+  if (chunk <= 0) chunk = 128;
+  if (chunk > n) chunk = n;
+  return chunk < 1 ? 1 : chunk;
+}
+
+}  // namespace hipac
+
+// ==========================================================================================
+// C ABI
+// ==========================================================================================
 using namespace hipac;
-extern "C" size_t hipac_resnet18_packed_bytes(int) { return 0; }
-extern "C" int hipac_resnet18_pack(const float* const*, int, int, float, void*, size_t) { set_error("stage 2 not built"); return -4; }
-extern "C" size_t hipac_resnet18_workspace_bytes(int, int) { return 0; }
-extern "C" int hipac_resnet18_forward(const void*, int, const void*, int, int, float*, float*, void*, size_t, int, void*) { set_error("stage 2 not built"); return -4; }
-extern "C" int hipac_resnet18_conv_layer(const void*, int, int, const void*, const void*, void*, int, int, void*) { set_error("stage 2 not built"); return -4; }
+
+extern "C" size_t hipac_resnet18_packed_bytes(int num_classes) { return packed_layout(num_classes).total; }
+
+extern "C" int hipac_resnet18_pack(const float* const* t, int num_tensors, int num_classes, float bn_eps, void* h_packed,
+                                   size_t packed_bytes) {
+  HIPAC_REQUIRE(num_tensors == HIPAC_RESNET18_NUM_TENSORS, "expected 102 tensors (20 x [conv, bn.w, bn.b, bn.mean, bn.var] + fc.w + fc.b)");
+  HIPAC_REQUIRE(num_classes >= 0 && num_classes <= 1024, "bad num_classes");
+  const PackedLayout L = packed_layout(num_classes);
+  HIPAC_REQUIRE(h_packed && packed_bytes >= L.total, "packed buffer too small");
+  memset(h_packed, 0, L.total);
+  uint8_t* dst = reinterpret_cast<uint8_t*>(h_packed);
+  for (int l = 0; l < HIPAC_RESNET18_NUM_CONVS; l++) {
+    const ConvSpec& cs = kConvs[l];
+    const float *w = t[5 * l], *g = t[5 * l + 1], *b = t[5 * l + 2], *mu = t[5 * l + 3], *var = t[5 * l + 4];
+    HIPAC_REQUIRE(w && g && b && mu && var, "null tensor");
+    uint16_t* wp = reinterpret_cast<uint16_t*>(dst + L.w_off[l]);
+    float* bp = reinterpret_cast<float*>(dst + L.b_off[l]);
+    const int K = conv_gemm_k(l);
+    for (int o = 0; o < cs.cout; o++) {
+      const float scale = g[o] / sqrtf(var[o] + bn_eps);  // eval-mode BN folded in fp32
+      bp[o] = b[o] - mu[o] * scale;
+      for (int c = 0; c < cs.cin; c++)
+        for (int r = 0; r < cs.k; r++)
+          for (int s = 0; s < cs.k; s++) {
+            const float v = w[(((size_t)o * cs.cin + c) * cs.k + r) * cs.k + s] * scale;
+            size_t kidx;
+            if (l == 0) {
+              // kh = 2a+dy-1, kw = 2b+dx-1 (filter padded to 8x8 with a zero first row/column)
+              const int a = (r + 1) >> 1, dy = (r + 1) & 1, bb = (s + 1) >> 1, dx = (s + 1) & 1;
+              kidx = (size_t)(a * 4 + bb) * 16 + (dy * 2 + dx) * 3 + c;
+            } else {
+              kidx = (size_t)(r * cs.k + s) * cs.cin + c;
+            }
+            wp[(size_t)o * K + kidx] = host_bf16(v);
+          }
+    }
+  }
+  if (num_classes > 0) {
+    const float *fw = t[100], *fb = t[101];
+    HIPAC_REQUIRE(fw && fb, "num_classes > 0 needs fc weight and bias");
+    memcpy(dst + L.fc_w_off, fw, (size_t)num_classes * 512 * 4);
+    memcpy(dst + L.fc_b_off, fb, (size_t)num_classes * 4);
+  }
+  return 0;
+}
+
+extern "C" size_t hipac_resnet18_workspace_bytes(int n_patches, int chunk) {
+  if (n_patches <= 0) return 256;
+  const size_t c = (size_t)clamp_chunk(chunk, n_patches);
+  return c * (kC1Bytes + 4 * kActBytes + kS2dBytes) + 6 * 1024;
+}
+
+extern "C" int hipac_resnet18_conv_layer(const void* d_packed, int num_classes, int layer, const void* d_in,
+                                         const void* d_residual, void* d_out, int n_patches, int relu, void* stream_) {
+  HIPAC_REQUIRE(d_packed && d_in && d_out, "null pointer");
+  HIPAC_REQUIRE(layer >= 0 && layer < HIPAC_RESNET18_NUM_CONVS, "layer index out of range");
+  HIPAC_REQUIRE(n_patches > 0, "n_patches must be positive");
+  if (int e = init_driver_api()) return e;
+  const PackedLayout L = packed_layout(num_classes);
+  return run_conv(reinterpret_cast<const uint8_t*>(d_packed), L, layer, d_in, d_residual, d_out, n_patches, relu != 0,
+                  (cudaStream_t)stream_);
+}
+
+extern "C" int hipac_resnet18_forward(const void* d_packed, int num_classes, const void* d_batch, int layout, int n_patches,
+                                      float* d_feats, float* d_logits, void* d_workspace, size_t workspace_bytes, int chunk,
+                                      void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  HIPAC_REQUIRE(n_patches >= 0, "negative n_patches");
+  if (n_patches == 0) return 0;
+  HIPAC_REQUIRE(d_packed && d_batch && d_feats && d_workspace, "null pointer");
+  HIPAC_REQUIRE(layout == HIPAC_LAYOUT_S2D16_BF16 || layout == HIPAC_LAYOUT_NHWC3_BF16, "unknown batch layout");
+  HIPAC_REQUIRE(!d_logits || num_classes > 0, "logits requested but the packed weights have no classifier head");
+  HIPAC_REQUIRE(workspace_bytes >= hipac_resnet18_workspace_bytes(n_patches, chunk), "workspace too small");
+  HIPAC_REQUIRE(((uintptr_t)d_workspace & 255) == 0, "workspace must be 256-byte aligned");
+  if (int e = init_driver_api()) return e;
+  const PackedLayout L = packed_layout(num_classes);
+  const uint8_t* pk = reinterpret_cast<const uint8_t*>(d_packed);
+  const int cmax = clamp_chunk(chunk, n_patches);
+  uint8_t* ws = reinterpret_cast<uint8_t*>(d_workspace);
+  auto carve = [&](size_t bytes) {
+    uint8_t* r = ws;
+    ws += align_up(bytes, 1024);
+    return r;
+  };
+  uint8_t* c1 = carve(cmax * kC1Bytes);
+  uint8_t* A = carve(cmax * kActBytes);
+  uint8_t* B = carve(cmax * kActBytes);
+  uint8_t* C = carve(cmax * kActBytes);
+  uint8_t* D = carve(cmax * kActBytes);
+  uint8_t* s2d = carve(cmax * kS2dBytes);
+
+  for (int i0 = 0; i0 < n_patches; i0 += cmax) {
+    const int n = n_patches - i0 < cmax ? n_patches - i0 : cmax;
+    const void* x0;
+    if (layout == HIPAC_LAYOUT_S2D16_BF16) {
+      x0 = reinterpret_cast<const uint8_t*>(d_batch) + (size_t)i0 * kS2dBytes;
+    } else {
+      const uint16_t* src = reinterpret_cast<const uint16_t*>(d_batch) + (size_t)i0 * 224 * 224 * 3;
+      k_pack_s2d16<<<g_num_sms * 8, 256, 0, stream>>>(src, reinterpret_cast<uint16_t*>(s2d), n);
+      count_launch(1);
+      x0 = s2d;
+    }
+    auto conv = [&](int layer, const void* in, const void* res, void* out, bool relu) {
+      return run_conv(pk, L, layer, in, res, out, n, relu, stream);
+    };
+    int e = 0;
+    if ((e = conv(0, x0, nullptr, c1, true))) return e;
+    k_maxpool<<<g_num_sms * 8, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(c1), reinterpret_cast<__nv_bfloat16*>(A), n);
+    count_launch(1);
+    // layer1 (two basic blocks, identity shortcuts)
+    if ((e = conv(1, A, nullptr, B, true)) || (e = conv(2, B, A, C, true))) return e;
+    if ((e = conv(3, C, nullptr, B, true)) || (e = conv(4, B, C, A, true))) return e;
+    // layer2..4: first block has a strided 1x1 projection shortcut
+    for (int s = 0; s < 3; s++) {
+      const int l0 = 5 + 5 * s;
+      if ((e = conv(l0, A, nullptr, B, true))) return e;           // 3x3 / stride 2
+      if ((e = conv(l0 + 2, A, nullptr, D, false))) return e;      // downsample 1x1 / stride 2 (+BN), no ReLU
+      if ((e = conv(l0 + 1, B, D, C, true))) return e;             // 3x3 + shortcut + ReLU
+      if ((e = conv(l0 + 3, C, nullptr, B, true)) || (e = conv(l0 + 4, B, C, A, true))) return e;
+    }
+    k_avgpool_fc<<<n, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(A), d_feats + (size_t)i0 * 512,
+                                        d_logits ? d_logits + (size_t)i0 * num_classes : nullptr,
+                                        reinterpret_cast<const float*>(pk + L.fc_w_off),
+                                        reinterpret_cast<const float*>(pk + L.fc_b_off), num_classes);
+    count_launch(1);
+  }
+  HIPAC_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}

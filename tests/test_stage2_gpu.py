@@ -1,0 +1,133 @@
+"""Stage-2 parity on the GPU: the tcgen05 ResNet18 kernels (through the C ABI) vs plain PyTorch fp32.
+
+Per-layer tests feed the SAME bf16-rounded operands to both sides, so only accumulation order and the
+final bf16 rounding differ (tolerance: 1.5 bf16 ulp of the layer's dynamic range).  End-to-end tests
+compare against the fp32 oracle / the golden vectors frozen from the reference with the tolerances
+BASELINE.json's north_star states: cosine >= 0.9995, max|d|/max|ref| <= 1e-2, argmax agreement >= 99.9 %."""
+import numpy as np
+import pytest
+
+from conftest import load_golden
+from oracle import hipac_oracle as orc
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+SPECS = [(3, 64, 7, 2, 3, 224)] + [(64, 64, 3, 1, 1, 56)] * 4 + \
+        [(64, 128, 3, 2, 1, 56), (128, 128, 3, 1, 1, 28), (64, 128, 1, 2, 0, 56), (128, 128, 3, 1, 1, 28), (128, 128, 3, 1, 1, 28)] + \
+        [(128, 256, 3, 2, 1, 28), (256, 256, 3, 1, 1, 14), (128, 256, 1, 2, 0, 28), (256, 256, 3, 1, 1, 14), (256, 256, 3, 1, 1, 14)] + \
+        [(256, 512, 3, 2, 1, 14), (512, 512, 3, 1, 1, 7), (256, 512, 1, 2, 0, 14), (512, 512, 3, 1, 1, 7), (512, 512, 3, 1, 1, 7)]
+
+
+@pytest.fixture(scope="module")
+def net_and_packed():
+    from ss25_hierarchical_multiscale_image_classification_b200 import features
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    net = orc.make_resnet18(seed=0, classifier=True)
+    packed = features.pack_resnet18(net.state_dict(), "cuda")
+    return net, packed
+
+
+def _folded(net, layer):
+    from ss25_hierarchical_multiscale_image_classification_b200 import features
+    conv, bn = features.conv_bn_names()[layer]
+    sd = net.state_dict()
+    scale = sd[f"{bn}.weight"] / torch.sqrt(sd[f"{bn}.running_var"] + 1e-5)
+    w = (sd[f"{conv}.weight"] * scale[:, None, None, None]).bfloat16().float()
+    b = sd[f"{bn}.bias"] - sd[f"{bn}.running_mean"] * scale
+    return w.cuda(), b.cuda()
+
+
+@pytest.mark.parametrize("n", [1, 3])
+@pytest.mark.parametrize("layer", list(range(20)))
+def test_conv_layer_vs_torch_fp32(net_and_packed, layer, n):
+    from ss25_hierarchical_multiscale_image_classification_b200 import features
+    net, packed = net_and_packed
+    cin, cout, k, stride, pad, hin = SPECS[layer]
+    g = torch.Generator(device="cuda").manual_seed(100 + layer)
+    x = torch.randn((n, hin, hin, cin), generator=g, device="cuda").bfloat16()
+    w, b = _folded(net, layer)
+    ref = torch.nn.functional.conv2d(x.float().permute(0, 3, 1, 2), w, b, stride=stride, padding=pad)
+    hout = ref.shape[-1]
+    use_res = layer in (2, 4, 6, 9, 11, 14, 16, 19)
+    res = torch.randn((n, hout, hout, cout), generator=g, device="cuda").bfloat16() if use_res else None
+    if res is not None:
+        ref = ref + res.float().permute(0, 3, 1, 2)
+    relu = layer not in (7, 12, 17)
+    if relu:
+        ref = torch.relu(ref)
+    if layer == 0:
+        xin = torch.zeros((n, 112, 112, 16), dtype=torch.bfloat16, device="cuda")
+        xin[..., :12] = x.reshape(n, 112, 2, 112, 2, 3).permute(0, 1, 3, 2, 4, 5).reshape(n, 112, 112, 12)
+    else:
+        xin = x
+    out = features.conv_layer(packed, layer, xin, res, relu)
+    torch.cuda.synchronize()
+    got = out.float().permute(0, 3, 1, 2)
+    scale = float(ref.abs().max())
+    err = float((got - ref).abs().max())
+    assert err <= 1.5 * 2.0 ** -8 * scale + 1e-3, f"layer {layer}: max err {err} at scale {scale}"
+
+
+def _metrics(got, ref):
+    cos = (got * ref).sum(1) / (np.linalg.norm(got, axis=1) * np.linalg.norm(ref, axis=1))
+    maxrel = np.abs(got - ref).max(1) / np.abs(ref).max(1)
+    return cos.min(), maxrel.max()
+
+
+def _gpu_features(packed, images_u8, layout):
+    from ss25_hierarchical_multiscale_image_classification_b200 import features
+    lut = torch.from_numpy(orc.normalize_lut()).cuda()
+    u8 = torch.from_numpy(images_u8).cuda().long()
+    x = torch.stack([lut[:, c][u8[..., c]] for c in range(3)], dim=-1).bfloat16()     # NHWC3 bf16
+    if layout == "s2d16":
+        n = x.shape[0]
+        y = torch.zeros((n, 112, 112, 16), dtype=torch.bfloat16, device="cuda")
+        y[..., :12] = x.reshape(n, 112, 2, 112, 2, 3).permute(0, 1, 3, 2, 4, 5).reshape(n, 112, 112, 12)
+        x = y
+    f, lg = features.classify_tensor(x, packed, chunk=5)
+    torch.cuda.synchronize()
+    return f.cpu().numpy(), lg.cpu().numpy()
+
+
+@pytest.mark.parametrize("layout", ["s2d16", "nhwc3"])
+def test_features_vs_golden_reference(net_and_packed, layout):
+    net, packed = net_and_packed
+    g = load_golden("stage2_features.npz")
+    feats, logits = _gpu_features(packed, g["images"], layout)
+    cos, maxrel = _metrics(feats, g["features"])
+    assert cos >= 0.9995 and maxrel <= 1e-2, (cos, maxrel)
+    assert np.array_equal(logits.argmax(1), g["logits"].argmax(1))
+
+
+def test_features_vs_fp32_oracle_random_patches(net_and_packed):
+    net, packed = net_and_packed
+    rng = np.random.default_rng(0)
+    n = 23                                                    # not a multiple of the chunk (5)
+    base = rng.integers(0, 256, size=(n, 28, 28, 3), dtype=np.uint8)
+    imgs = np.repeat(np.repeat(base, 8, axis=1), 8, axis=2)  # blocky structure + noise
+    imgs = np.clip(imgs.astype(np.int32) + rng.integers(-20, 21, size=imgs.shape), 0, 255).astype(np.uint8)
+    ref_f, ref_l = orc.resnet18_features_fp32(net, imgs)
+    feats, logits = _gpu_features(packed, imgs, "s2d16")
+    cos, maxrel = _metrics(feats, ref_f)
+    assert cos >= 0.9995 and maxrel <= 1e-2, (cos, maxrel)
+    margin = np.abs(ref_l[:, 0] - ref_l[:, 1])
+    agree = (logits.argmax(1) == ref_l.argmax(1)) | (margin < 1e-3 * np.abs(ref_l).max())
+    assert agree.mean() >= 0.999
+
+
+def test_headless_packed_weights_and_errors():
+    from ss25_hierarchical_multiscale_image_classification_b200 import features
+    net = orc.make_resnet18(seed=1, classifier=False)
+    sd = {k: v for k, v in net.state_dict().items() if not k.startswith("fc.")}
+    packed = features.pack_resnet18(sd, "cuda")
+    assert packed.num_classes == 0
+    x = torch.zeros((2, 112, 112, 16), dtype=torch.bfloat16, device="cuda")
+    f = features.extract_features_tensor(x, packed)
+    assert f.shape == (2, 512) and torch.isfinite(f).all()
+    with pytest.raises(ValueError):
+        features.classify_tensor(x, packed)
+    with pytest.raises(ValueError):
+        features.extract_features_tensor(x.float(), packed)
+    assert features.extract_features_tensor(x[:0], packed).shape == (0, 512)
