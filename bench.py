@@ -1,0 +1,377 @@
+#!/usr/bin/env python
+"""HiPAC hot-path benchmark: patches/sec through tile + tissue/lesion mask + ResNet18 features.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (BASELINE.json configs[1]): a synthetic level-0 image, 16384 x 16384 RGB per GPU, tiled
+into 1792^2 patches on the reference CLI's 224-px grid (src/main.py:611 -> stride 224 at every
+level), white-padded borders, mean>240 tissue rejection, lesion-mask labels, Pillow-exact resize to
+224^2, ImageNet normalisation, then ResNet18 512-d features + 2-class logits for every survivor.
+A "step" is one pass over the whole level image.  With N > 1 the slide is N x 16384 rows tall and is
+sharded by candidate tile-row range across the ranks (weak scaling: per-GPU work fixed); the only
+collective is the NCCL all-gather of survivor counts / coordinates / labels / features.
+
+Prints ONE JSON line (rank 0).  `value` = survivors (patches that get features) per second over all
+ranks with the image resident in HBM; `e2e` = same through host buffers (pinned H2D of the image and
+mask, D2H of coords / labels / features inside the timed region).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+LEVEL, PATCH, STRIDE = 0, 1792, 224
+WIDTH, ROWS_PER_GPU = 16384, 16384
+SEED = 1234
+FLOP_PER_PATCH = 3.627e9          # SURVEY.md section 2.2 (conv 2*MAC + fc)
+S2D_BYTES = 112 * 112 * 16 * 2
+
+
+def measured_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self._stop = index, [], threading.Event()
+        self._t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
+                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+def shard_rows(ny_total: int, world: int, rank: int):
+    """Contiguous candidate tile-row range of `rank` (balanced by row count)."""
+    base, rem = divmod(ny_total, world)
+    i0 = rank * base + min(rank, rem)
+    return i0, i0 + base + (1 if rank < rem else 0)
+
+
+def build_slab(world: int, rank: int):
+    """Pinned host tensors of this rank's row slab (+ halo) of the N x 16384-row synthetic slide."""
+    import torch
+    from ss25_hierarchical_multiscale_image_classification_b200.synthetic import make_lesion_mask, make_level
+    H = ROWS_PER_GPU * world
+    ny_total = (H + STRIDE - 1) // STRIDE
+    i0, i1 = shard_rows(ny_total, world, rank)
+    y0, y1 = i0 * STRIDE, min(H, (i1 - 1) * STRIDE + PATCH)
+    img = torch.empty((y1 - y0, WIDTH, 3), dtype=torch.uint8).pin_memory()
+    msk = torch.empty((y1 - y0, WIDTH), dtype=torch.uint8).pin_memory()
+    inp, mnp = img.numpy(), msk.numpy()
+
+    def fill(r):
+        r1 = min(r + 256, y1)
+        inp[r - y0:r1 - y0] = make_level(SEED, LEVEL, WIDTH, H, r, r1)
+        mnp[r - y0:r1 - y0] = make_lesion_mask(SEED, LEVEL, WIDTH, H, r, r1)
+
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max(1, min(16, (os.cpu_count() or 8) // max(1, world)))) as ex:
+        list(ex.map(fill, range(y0, y1, 256)))
+    return img, msk, (i0, i1, y0, H)
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as ge
+    from oracle import hipac_oracle as orc   # weights recipe only (seeded torchvision resnet18)
+    from ss25_hierarchical_multiscale_image_classification_b200 import _lib, features
+    from ss25_hierarchical_multiscale_image_classification_b200.preprocessing import extract_patches_tensor
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    ge.build()
+    net = orc.make_resnet18(seed=0, classifier=True)                      # random-init weights (BASELINE config)
+    packed = features.pack_resnet18(net.state_dict(), dev)
+    img_h, msk_h, (i0, i1, y0, H) = build_slab(world, rank)
+    img_d, msk_d = img_h.to(dev), msk_h.to(dev)
+    rows = (0, i1 - i0)
+    n_cand = ((WIDTH + STRIDE - 1) // STRIDE) * (i1 - i0)
+    cap = n_cand
+    # persistent host/device buffers for the e2e leg
+    img_e, msk_e = torch.empty_like(img_d), torch.empty_like(msk_d)
+    h_feats = torch.empty((cap, 512), dtype=torch.float32).pin_memory()
+    h_coords = torch.empty((cap, 2), dtype=torch.int32).pin_memory()
+    h_labels = torch.empty((cap,), dtype=torch.uint8).pin_memory()
+
+    def gather(pb, feats, logits):
+        if world == 1:
+            return len(pb)
+        cnt = torch.tensor([len(pb)], dtype=torch.int64, device=dev)
+        counts = [torch.zeros_like(cnt) for _ in range(world)]
+        dist.all_gather(counts, cnt)
+        mx = int(max(int(c) for c in counts))
+        def pad(t):
+            out = torch.zeros((mx,) + tuple(t.shape[1:]), dtype=t.dtype, device=dev)
+            out[:t.shape[0]] = t
+            return out
+        coords = pb.coords.clone()
+        coords[:, 1] += y0
+        for t in (coords, pb.labels, feats, logits):
+            buf = torch.empty((world * mx,) + tuple(t.shape[1:]), dtype=t.dtype, device=dev)
+            dist.all_gather_into_tensor(buf, pad(t))
+        return int(sum(int(c) for c in counts))
+
+    def step_resident():
+        pb = extract_patches_tensor(img_d, msk_d, LEVEL, stride=None, row_range=rows, layout="s2d16", capacity=cap)
+        feats, logits = features.classify_tensor(pb.batch, packed, chunk=args.chunk)
+        return gather(pb, feats, logits), pb
+
+    def step_e2e():
+        img_e.copy_(img_h, non_blocking=True)
+        msk_e.copy_(msk_h, non_blocking=True)
+        pb = extract_patches_tensor(img_e, msk_e, LEVEL, stride=None, row_range=rows, layout="s2d16", capacity=cap)
+        feats, logits = features.classify_tensor(pb.batch, packed, chunk=args.chunk)
+        total = gather(pb, feats, logits)
+        n = len(pb)
+        h_feats[:n].copy_(feats, non_blocking=True)
+        h_coords[:n].copy_(pb.coords, non_blocking=True)
+        h_labels[:n].copy_(pb.labels, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return total, pb
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            total, pb = fn()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            total, pb = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms) / steps, total, pb
+
+    _lib.lib().hipac_launch_count(1)
+    with ClockSampler(local) as clk:
+        ms_step, total_surv, pb = timed(step_resident, args.steps, args.warmup)
+    launches = int(_lib.lib().hipac_launch_count(1)) // (args.steps + args.warmup)
+    ms_e2e, total_surv_e, _ = timed(step_e2e, max(2, args.steps // 2), 1)
+    n_surv = len(pb)
+
+    # per-kernel CUDA-event timing (library profiler) over 2 extra steps, off the timed region
+    _lib.profile(True)
+    for _ in range(2):
+        step_resident()
+    torch.cuda.synchronize()
+    prof = _lib.profile_report()
+    _lib.profile(False)
+    peaks, peak_src = measured_peaks()
+    conv = {k: v for k, v in prof.items() if k.startswith("conv")}
+    conv_ms = sum(v["ms"] for v in conv.values())
+    conv_flops = sum(v["work"] for v in conv.values())
+    conv_tf = conv_flops / (conv_ms * 1e-3) / 1e12 if conv_ms else 0.0
+    s1 = {k: v for k, v in prof.items() if not k.startswith(("conv", "maxpool", "avgpool", "pack"))}
+    s1_ms = sum(v["ms"] for v in s1.values()) / 2
+    s1_bytes = img_d.numel() + msk_d.numel() + n_surv * (S2D_BYTES + 9)
+    kernels = {k: {"launches_per_step": v["launches"] // 2, "ms_per_step": round(v["ms"] / 2, 4),
+                   **({"tflops": round(v["work"] / (v["ms"] * 1e-3) / 1e12, 1)} if k.startswith("conv") and v["ms"] else {})}
+               for k, v in prof.items()}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    cpu = cpu_baseline_sample(step=0, budget_candidates=args.cpu_candidates) if world == 1 and not args.no_cpu else None
+    out = {
+        "metric": "patches/sec (tile+mask+ResNet18 features)",
+        "value": round(total_surv / (ms_step * 1e-3), 1),
+        "unit": "patches/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": round(ms_step, 3),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u8 (tiling/mask/resample, bit-exact) + bf16 tensor-core convs with fp32 accumulate",
+        "data": "synthetic (counter-hash slide, seeded random-init ResNet18)",
+        "config": {"workload": "configs[1]: level-0 16384x16384 RGB per GPU, P=1792 patches on the 224-px CLI grid, "
+                               "tissue mean>240 rejection + lesion-mask labels + Pillow-exact resize + ResNet18 features/logits",
+                   "level": LEVEL, "patch": PATCH, "stride": STRIDE, "width": WIDTH, "rows_per_gpu": ROWS_PER_GPU,
+                   "candidates_per_step": n_cand * world if world == 1 else None, "survivors_per_step": total_surv,
+                   "candidates_per_s": round(n_cand * world / (ms_step * 1e-3), 1),
+                   "sharding": f"tile-row ranges over {world} rank(s); NCCL all-gather of counts/coords/labels/features",
+                   "cache": "inputs (0.8 GB image + 0.27 GB mask per GPU) exceed the 126 MB L2; no flush needed",
+                   "resnet_chunk": args.chunk},
+        "e2e": {"value": round(total_surv_e / (ms_e2e * 1e-3), 1), "unit": "patches/s",
+                "h2d_bytes_per_step": int(img_h.numel() + msk_h.numel()),
+                "d2h_bytes_per_step": int(n_surv * (512 * 4 + 8 + 1) + 8), "ms_per_step": round(ms_e2e, 3)},
+        "gpu_launches": launches,
+        "clocks": clk.summary(),
+        "roofline": {"bound": "tensor", "kernel": "k_conv_umma (all 20 conv layers)", "achieved": round(conv_tf, 1),
+                     "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                     "frac": round(conv_tf / peaks["bf16_tflops_sustained"], 4), "traffic": None, "peak_source": peak_src,
+                     "conv_ms_per_step": round(conv_ms / 2, 3)},
+        "roofline_stage1": {"bound": "hbm", "kernel": "stage-1 tile scan (all kernels)",
+                            "achieved": round(s1_bytes / (s1_ms * 1e-3) / 1e9, 1) if s1_ms else None,
+                            "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                            "frac": round(s1_bytes / (s1_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], 4) if s1_ms else None,
+                            "ms_per_step": round(s1_ms, 3), "algorithmic_bytes": int(s1_bytes)},
+        "kernels": kernels,
+    }
+    if cpu:
+        out["cpu_baseline"] = cpu
+    print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_sample_regions(budget_candidates: int):
+    """Every-k-th candidate of the N=1 workload with its source pixels pre-generated (so synthetic-data
+    generation is NOT timed as reference work; the reference would get them from read_region)."""
+    from concurrent.futures import ThreadPoolExecutor
+    from ss25_hierarchical_multiscale_image_classification_b200.synthetic import make_lesion_mask, make_level
+    H = ROWS_PER_GPU
+    nx, ny = (WIDTH + STRIDE - 1) // STRIDE, (H + STRIDE - 1) // STRIDE
+    k = max(1, (nx * ny) // budget_candidates)
+    cands = [(ix * STRIDE, iy * STRIDE) for ix in range(nx) for iy in range(ny)]
+    sample = cands[k // 2::k][:budget_candidates]
+
+    def gen(xy):
+        x, y = xy
+        w, h = min(PATCH, WIDTH - x), min(PATCH, H - y)
+        return xy, (make_level(SEED, LEVEL, WIDTH, H, y, y + h, x, x + w),
+                    make_lesion_mask(SEED, LEVEL, WIDTH, H, y, y + h)[:, x:x + w])
+
+    with ThreadPoolExecutor(min(16, os.cpu_count() or 8)) as ex:
+        cache = dict(ex.map(gen, sample))
+    return sample, cache, k
+
+
+def cpu_baseline_sample(step: int, budget_candidates: int, regions=None):
+    """Time the CPU port of the reference path on an every-k-th-candidate sample of the N=1 workload."""
+    import torch
+    from oracle import cpu_pipeline, hipac_oracle as orc
+
+    H = ROWS_PER_GPU
+    sample, cache, k = regions or cpu_sample_regions(budget_candidates)
+    net = orc.make_resnet18(seed=0, classifier=True)
+
+    from PIL import Image
+    t0 = time.perf_counter()
+    patches, n_c = [], 0
+    for (x, y) in sample:                                      # the reference's per-candidate body (src/main.py:688-727)
+        n_c += 1
+        rgb, m = cache[(x, y)]
+        region = Image.fromarray(np.dstack([rgb, np.full(rgb.shape[:2], 255, np.uint8)]), "RGBA").convert("RGB")
+        if region.size != (PATCH, PATCH):
+            padded = Image.new("RGB", (PATCH, PATCH), (255, 255, 255))
+            padded.paste(region, (0, 0))
+            region = padded
+        mask_patch = Image.fromarray(m, "L").crop((0, 0, PATCH, PATCH))
+        _label = 1 if np.any(np.array(mask_patch) > 0) else 0
+        if np.mean(np.array(region)) > 240:
+            continue
+        patches.append(region)
+    t1 = time.perf_counter()
+    feats = cpu_pipeline.stage2_reference_loop(patches, net, batch=64)
+    t2 = time.perf_counter()
+    total = t2 - t0
+    return {"value": round(len(patches) / total, 2), "unit": "patches/s", "cores": int(torch.get_num_threads()),
+            "kind": "port",
+            "sample": f"every {k}-th candidate of the N=1 workload: {n_c} candidates -> {len(patches)} survivors; "
+                      f"stage 1 (single thread, as the reference; no PNG write) {t1 - t0:.2f} s, stage 2 (Resize+ToTensor+"
+                      f"Normalize per patch, fp32 ResNet18 on {torch.get_num_threads()} threads, batch 64) {t2 - t1:.2f} s",
+            "candidates_per_s": round(n_c / total, 2), "host_cpus": os.cpu_count(),
+            "feature_checksum": float(np.abs(feats).sum())}
+
+
+def run_reference(args):
+    """`--impl reference`: the CPU port of the reference path on host cores, bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    vals, last = [], None
+    regions = cpu_sample_regions(args.cpu_candidates)
+    for s in range(args.warmup + args.steps):
+        r = cpu_baseline_sample(step=s, budget_candidates=args.cpu_candidates, regions=regions)
+        if s >= args.warmup:
+            vals.append(r)
+        last = r
+    tot_surv = sum(float(v["value"]) for v in vals) / len(vals)
+    out = {"impl": "reference", "metric": "patches/sec (tile+mask+ResNet18 features)", "value": round(tot_surv, 2),
+           "unit": "patches/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "u8 + fp32 (CPU)", "data": "synthetic (same slide and weights as the GPU arm)",
+           "config": {"workload": "configs[1] (bounded every-k-th-candidate sample per step), CPU port of the reference path",
+                      "level": LEVEL, "patch": PATCH, "stride": STRIDE, "width": WIDTH, "rows_per_gpu": ROWS_PER_GPU},
+           "cpu_baseline": {**last, "value": round(tot_surv, 2)},
+           "e2e": {"value": round(tot_surv, 2), "unit": "patches/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--chunk", type=int, default=128, help="patches per ResNet18 chunk")
+    ap.add_argument("--cpu-candidates", type=int, default=96, help="candidates in the bounded CPU-baseline sample")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

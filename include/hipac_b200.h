@@ -116,6 +116,13 @@ int hipac_resnet18_conv_layer(const void* d_packed, int num_classes, int layer,
  * (bench.py's "gpu_launches"). */
 long long hipac_launch_count(int reset);
 
+/* Optional per-kernel profiler (calling thread): when enabled every kernel launch of the library is
+ * bracketed by CUDA events on its stream.  hipac_profile_report synchronises them, writes one line per
+ * kernel "<name> <launches> <total_ms> <total_work>" (work = algorithmic bytes for the stage-1 kernels,
+ * flops for the conv kernels), clears the records and returns the report length. */
+int hipac_profile_enable(int on);
+long long hipac_profile_report(char* buf, size_t cap);
+
 #ifdef __cplusplus
 }
 #endif

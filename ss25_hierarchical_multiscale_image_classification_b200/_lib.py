@@ -97,6 +97,10 @@ def _declare(l):
     l.hipac_resnet18_workspace_bytes.argtypes = [i32, i32]
     l.hipac_resnet18_forward.restype = i32
     l.hipac_resnet18_forward.argtypes = [vp, i32, vp, i32, i32, vp, vp, vp, sz, i32, vp]
+    l.hipac_profile_enable.restype = i32
+    l.hipac_profile_enable.argtypes = [i32]
+    l.hipac_profile_report.restype = C.c_longlong
+    l.hipac_profile_report.argtypes = [C.c_char_p, sz]
     l.hipac_resnet18_conv_layer.restype = i32
     l.hipac_resnet18_conv_layer.argtypes = [vp, i32, i32, vp, vp, vp, i32, i32, vp]
 
@@ -105,7 +109,7 @@ EXPORTS = [
     "hipac_last_error", "hipac_abi_version", "hipac_launch_count", "hipac_tile_scan_workspace_bytes",
     "hipac_tile_scan", "hipac_pillow_coeffs", "hipac_normalize_lut_bf16", "hipac_resnet18_packed_bytes",
     "hipac_resnet18_pack", "hipac_resnet18_workspace_bytes", "hipac_resnet18_forward",
-    "hipac_resnet18_conv_layer",
+    "hipac_resnet18_conv_layer", "hipac_profile_enable", "hipac_profile_report",
 ]
 
 
@@ -127,3 +131,20 @@ def lib():
 def check(rc: int, what: str):
     if rc != 0:
         raise RuntimeError(f"{what} failed ({rc}): {lib().hipac_last_error().decode()}")
+
+
+def profile(enable: bool):
+    """Switch the library's per-kernel CUDA-event profiler on or off (calling thread)."""
+    lib().hipac_profile_enable(int(enable))
+
+
+def profile_report() -> dict:
+    """``{kernel: {"launches": n, "ms": total_ms, "work": bytes_or_flops}}`` since the last report."""
+    l = lib()
+    buf = C.create_string_buffer(1 << 16)
+    l.hipac_profile_report(buf, len(buf))
+    out = {}
+    for line in buf.value.decode().splitlines():
+        name, n, ms, work = line.split()
+        out[name] = {"launches": int(n), "ms": float(ms), "work": float(work)}
+    return out

@@ -4,6 +4,7 @@
 #include <cuda_bf16.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <string.h>
 #include <string>
 
 #include "../../include/hipac_b200.h"
@@ -12,6 +13,16 @@ namespace hipac {
 
 void set_error(const std::string& msg);
 void count_launch(int n = 1);
+
+// RAII CUDA-event bracket around one kernel launch; a no-op unless hipac_profile_enable(1).
+class ProfileScope {
+ public:
+  ProfileScope(const char* name, cudaStream_t stream, double work = 0.0);
+  ~ProfileScope();
+ private:
+  int idx_;
+  cudaStream_t stream_;
+};
 
 #define HIPAC_CHECK_CUDA(expr)                                                              \
   do {                                                                                      \

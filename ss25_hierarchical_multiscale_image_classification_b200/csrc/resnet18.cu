@@ -357,7 +357,8 @@ static int make_weight_map(CUtensorMap* map, const void* ptr, int cout, int K, i
 }
 
 template <int BN, bool CONV1>
-static int launch_conv_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvParams& p, cudaStream_t stream) {
+static int launch_conv_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvParams& p, cudaStream_t stream,
+                         const char* name, double flops) {
   using Cfg = ConvCfg<BN>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -366,7 +367,10 @@ static int launch_conv_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const C
   }
   const int tiles = p.num_m_tiles * p.num_n_tiles;
   const int grid = tiles < g_num_sms ? tiles : g_num_sms;
-  k_conv_umma<BN, CONV1><<<grid, kConvThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, p);
+  {
+    ProfileScope ps(name, stream, flops);
+    k_conv_umma<BN, CONV1><<<grid, kConvThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, p);
+  }
   count_launch(1);
   HIPAC_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -394,12 +398,18 @@ static int run_conv(const uint8_t* d_packed, const PackedLayout& L, int layer, c
     // 7x7/s2/p3 over 3 channels == 4x4/s1 over the 2x2 space-to-depth image (16 ch), pad 2 before / 1 after
     p.stride = 1, p.pad = 2, p.kw = 4, p.kc_blocks = 1, p.num_kb = 4;
     if (int e = make_im2col_map(&tmA, in, n, 112, 112, 16, 16, 4, 1, 2, 1, CU_TENSOR_MAP_SWIZZLE_32B)) return e;
-    return launch_conv_t<64, true>(tmA, tmB, p, stream);
+    return launch_conv_t<64, true>(tmA, tmB, p, stream, "conv1_7x7s2_c64", 2.0 * p.M_total * 64 * 147);
   }
   p.stride = cs.stride, p.pad = cs.pad, p.kw = cs.k, p.kc_blocks = cs.cin / 64, p.num_kb = cs.k * cs.k * p.kc_blocks;
   if (int e = make_im2col_map(&tmA, in, n, cs.hin, cs.hin, cs.cin, 64, cs.k, cs.stride, cs.pad, cs.pad, CU_TENSOR_MAP_SWIZZLE_128B))
     return e;
-  return bn == 128 ? launch_conv_t<128, false>(tmA, tmB, p, stream) : launch_conv_t<64, false>(tmA, tmB, p, stream);
+  static const char* kNames[4][2] = {{"conv3x3_c64", "conv1x1_c64"}, {"conv3x3_c128", "conv1x1_c128"},
+                                     {"conv3x3_c256", "conv1x1_c256"}, {"conv3x3_c512", "conv1x1_c512"}};
+  const int gi = cs.cout == 64 ? 0 : cs.cout == 128 ? 1 : cs.cout == 256 ? 2 : 3;
+  const char* name = kNames[gi][cs.k == 1 ? 1 : 0];
+  const double flops = 2.0 * p.M_total * cs.cout * K;
+  return bn == 128 ? launch_conv_t<128, false>(tmA, tmB, p, stream, name, flops)
+                   : launch_conv_t<64, false>(tmA, tmB, p, stream, name, flops);
 }
 
 static uint16_t host_bf16(float f) {
@@ -525,7 +535,10 @@ extern "C" int hipac_resnet18_forward(const void* d_packed, int num_classes, con
       x0 = reinterpret_cast<const uint8_t*>(d_batch) + (size_t)i0 * kS2dBytes;
     } else {
       const uint16_t* src = reinterpret_cast<const uint16_t*>(d_batch) + (size_t)i0 * 224 * 224 * 3;
-      k_pack_s2d16<<<g_num_sms * 8, 256, 0, stream>>>(src, reinterpret_cast<uint16_t*>(s2d), n);
+      {
+        ProfileScope ps("pack_s2d16", stream, (double)n * (224 * 224 * 3 * 2 + kS2dBytes));
+        k_pack_s2d16<<<g_num_sms * 8, 256, 0, stream>>>(src, reinterpret_cast<uint16_t*>(s2d), n);
+      }
       count_launch(1);
       x0 = s2d;
     }
@@ -534,7 +547,10 @@ extern "C" int hipac_resnet18_forward(const void* d_packed, int num_classes, con
     };
     int e = 0;
     if ((e = conv(0, x0, nullptr, c1, true))) return e;
-    k_maxpool<<<g_num_sms * 8, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(c1), reinterpret_cast<__nv_bfloat16*>(A), n);
+    {
+      ProfileScope ps("maxpool3x3s2", stream, (double)n * (kC1Bytes + kActBytes));
+      k_maxpool<<<g_num_sms * 8, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(c1), reinterpret_cast<__nv_bfloat16*>(A), n);
+    }
     count_launch(1);
     // layer1 (two basic blocks, identity shortcuts)
     if ((e = conv(1, A, nullptr, B, true)) || (e = conv(2, B, A, C, true))) return e;
@@ -547,6 +563,7 @@ extern "C" int hipac_resnet18_forward(const void* d_packed, int num_classes, con
       if ((e = conv(l0 + 1, B, D, C, true))) return e;             // 3x3 + shortcut + ReLU
       if ((e = conv(l0 + 3, C, nullptr, B, true)) || (e = conv(l0 + 4, B, C, A, true))) return e;
     }
+    ProfileScope ps_pool("avgpool_fc", stream, (double)n * (49 * 512 * 2 + 512 * 4));
     k_avgpool_fc<<<n, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(A), d_feats + (size_t)i0 * 512,
                                         d_logits ? d_logits + (size_t)i0 * num_classes : nullptr,
                                         reinterpret_cast<const float*>(pk + L.fc_w_off),

@@ -364,11 +364,18 @@ extern "C" int hipac_tile_scan(const uint8_t* d_rgb, int H, int W, int64_t pitch
   if (use_fused) {
     return fused_scan(p, o, flags, src_idx, d_coords, d_labels, d_count, capacity, ws, stream);
   }
-  k_stats_direct<<<n_cand, 256, 0, stream>>>(p, flags);
-  k_compact<<<1, 1024, 0, stream>>>(p, flags, n_cand, d_coords, d_labels, src_idx, d_count, capacity);
+  {
+    ProfileScope ps("stats_direct", stream, 0.0);
+    k_stats_direct<<<n_cand, 256, 0, stream>>>(p, flags);
+  }
+  {
+    ProfileScope ps("compact", stream, (double)n_cand);
+    k_compact<<<1, 1024, 0, stream>>>(p, flags, n_cand, d_coords, d_labels, src_idx, d_count, capacity);
+  }
   count_launch(2);
   if ((d_batch_u8 || d_batch) && capacity > 0) {
     dim3 grid((unsigned)min(n_cand, capacity), OUT);
+    ProfileScope ps("resample_direct", stream, 0.0);
     k_resample_direct<<<grid, 256, 0, stream>>>(p, o, d_coords, d_count, capacity);
     count_launch(1);
   }
