@@ -13,7 +13,7 @@ import threading
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libhipac_b200.so")
-SOURCES = ["capi.cu", "tile_scan.cu", "tile_scan_fused.cu", "resnet18.cu"]
+SOURCES = ["capi.cu", "tile_scan.cu", "resnet18.cu"]
 HEADER = os.path.join(os.path.dirname(_HERE), "include", "hipac_b200.h")
 
 LAYOUT_NHWC3_BF16 = 1

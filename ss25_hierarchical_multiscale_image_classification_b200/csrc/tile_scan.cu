@@ -281,6 +281,8 @@ __global__ void __launch_bounds__(256) k_resample_direct(ScanParams p, OutParams
   write_s2d_pad(o, slot, j);
 }
 
+#include "tile_scan_fused.cuh"
+
 }  // namespace hipac
 
 // ==========================================================================================
@@ -318,7 +320,11 @@ extern "C" size_t hipac_tile_scan_workspace_bytes(int H, int W, int P, int S, in
   if (scan_geometry(H, W, P, S, iy_begin, iy_end, &nx, &ny)) return 0;
   const size_t n_cand = (size_t)nx * ny;
   size_t b = align_up(n_cand, 256) + align_up(n_cand * 4, 256);  // flags + src_idx
-  b += fused_workspace_bytes(H, W, P, S, iy_begin, iy_end, mode);
+  if (mode != HIPAC_SCAN_DIRECT) {
+    ScanParams p{};
+    p.H = H, p.W = W, p.P = P, p.S = S, p.nx = nx, p.ny = ny, p.iy_begin = iy_begin;
+    b += fused_workspace_bytes_impl(p);
+  }
   return b + 256;
 }
 
@@ -337,10 +343,7 @@ extern "C" int hipac_tile_scan(const uint8_t* d_rgb, int H, int W, int64_t pitch
   HIPAC_REQUIRE(((uintptr_t)d_workspace & 255) == 0, "workspace must be 256-byte aligned");
   HIPAC_REQUIRE(workspace_bytes >= hipac_tile_scan_workspace_bytes(H, W, P, S, iy_begin, iy_end, mode), "workspace too small");
   HIPAC_REQUIRE((int64_t)nx * ny < (int64_t)1 << 30, "too many candidates for one call; split the row range");
-  const int f = P / OUT;
-  const bool fused_ok = (S % f) == 0;
   HIPAC_REQUIRE(mode == HIPAC_SCAN_AUTO || mode == HIPAC_SCAN_DIRECT || mode == HIPAC_SCAN_FUSED, "unknown scan mode");
-  HIPAC_REQUIRE(mode != HIPAC_SCAN_FUSED || fused_ok, "fused scan needs stride % (P/224) == 0");
   if (int e = upload_constants(stream)) return e;
 
   ScanParams p;
@@ -360,9 +363,12 @@ extern "C" int hipac_tile_scan(const uint8_t* d_rgb, int H, int W, int64_t pitch
     HIPAC_CHECK_CUDA(cudaMemsetAsync(d_count, 0, 8, stream));
     return 0;
   }
-  const bool use_fused = mode == HIPAC_SCAN_FUSED || (mode == HIPAC_SCAN_AUTO && fused_ok && fused_available());
-  if (use_fused) {
-    return fused_scan(p, o, flags, src_idx, d_coords, d_labels, d_count, capacity, ws, stream);
+  FusedGeom geom;
+  const bool fused_ok = n_cand > 0 && fused_geometry(p, &geom) && ((uintptr_t)d_rgb & 15) == 0;
+  HIPAC_REQUIRE(mode != HIPAC_SCAN_FUSED || fused_ok,
+                "fused scan needs stride % (P/224) == 0, gcd(stride, P) % 32 == 0 and a 16-byte aligned image");
+  if (mode != HIPAC_SCAN_DIRECT && fused_ok) {
+    return fused_scan_impl(p, o, flags, src_idx, d_coords, d_labels, d_count, capacity, ws, stream);
   }
   {
     ProfileScope ps("stats_direct", stream, 0.0);

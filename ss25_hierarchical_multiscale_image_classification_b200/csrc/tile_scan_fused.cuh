@@ -1,0 +1,457 @@
+// Read-once ("fused") stage-1 path.  Included by tile_scan.cu inside namespace hipac (shares its
+// __constant__ tables and helpers).
+//
+// With stride S a multiple of the scale f = P/224, every patch origin lies on the global f-grid, so the
+// Pillow-resampled patch equals a 224x224 crop of ONE globally resampled level image D -- except its
+// outer ring (output row/column 0 and 223), where Pillow clamps the filter window at the PATCH edge
+// (3f/2 taps, renormalised) instead of using the 2f-tap interior window (hard part 2).
+// Ring rows/columns of all patches fall on a fixed sub-lattice of D (rows k*S/f and k*S/f+223), so the
+// streaming pass also emits those rows/columns with the clamped coefficient sets ("variant planes").
+//
+//   k_cell_stats        one pass over the image (+mask): byte sums / lesion votes per g x g cell, g = gcd(S,P)
+//   k_patch_flags       patch sum = sum of its (P/g)^2 cells + white padding -> keep flag + label
+//   k_compact           (shared with the direct path) stable compaction in emission order
+//   k_downsample_planes one pass over the image: D and its 8 ring-variant planes (skipped when f == 1)
+//   k_gather            per survivor: 224x224 crop of the planes -> uint8 / normalised bf16 batch
+//
+// White padding: pixels right of / below the image read as 255 everywhere (the reference pastes partial
+// regions on a white canvas, src/main.py:700-703), which is consistent across all patches because patches
+// only ever extend past the right / bottom image edge.
+#pragma once
+
+struct FusedGeom {
+  int f, lf, Sf, g;        // scale, log2(scale), stride in D pixels, cell size
+  int ncx, cy0, ncy;       // cell grid: columns, first stored cell row (global index), stored rows
+  int Jbase, Dh, Dw;       // stored D rows [Jbase, Jbase+Dh) and columns [0, Dw)
+  int iy_begin, nx, ny;    // candidate grid of this call
+  uint32_t* cell_sum;      // [ncy][ncx]
+  uint32_t* cell_any;      // [ncy][ncx]
+  uint8_t* plane[3][3];    // [vkind][hkind], kinds: 0 interior, 1 top/left clamp, 2 bottom/right clamp
+};
+
+static inline int gcd_int(int a, int b) {
+  while (b) {
+    int t = a % b;
+    a = b, b = t;
+  }
+  return a;
+}
+
+// D-columns per CTA band and D-rows per CTA of k_downsample_planes: a 512 x 224 pixel image tile.
+__host__ __device__ constexpr int plane_ci(int f) { return 512 / f; }
+__host__ __device__ constexpr int plane_rj(int f) { return 224 / f; }
+__host__ __device__ constexpr int plane_ipt(int f) { return f == 8 ? 1 : (f == 4 ? 2 : 4); }
+
+static bool fused_geometry(const ScanParams& p, FusedGeom* G) {
+  const int f = p.P / OUT;
+  if (p.S % f) return false;
+  G->f = f, G->lf = f == 1 ? 0 : (f == 2 ? 1 : (f == 4 ? 2 : 3)), G->Sf = p.S / f;
+  G->g = gcd_int(p.S, p.P);
+  if (G->g % 32) return false;
+  G->iy_begin = p.iy_begin, G->nx = p.nx, G->ny = p.ny;
+  G->ncx = (p.W + G->g - 1) / G->g;
+  const int ncy_all = (p.H + G->g - 1) / G->g;
+  G->cy0 = (int)((int64_t)p.iy_begin * p.S / G->g);
+  int cy1 = (int)(((int64_t)(p.iy_begin + p.ny - 1) * p.S + p.P) / G->g);
+  if (cy1 > ncy_all) cy1 = ncy_all;
+  G->ncy = cy1 > G->cy0 ? cy1 - G->cy0 : 0;
+  G->Jbase = p.iy_begin * G->Sf;
+  const int jend = (p.iy_begin + p.ny - 1) * G->Sf + OUT;
+  const int jimg = (p.H + f / 2 + f - 1) / f;
+  G->Dh = (jend < jimg ? jend : jimg) - G->Jbase;
+  const int iend = (p.nx - 1) * G->Sf + OUT;
+  const int iimg = (p.W + f / 2 + f - 1) / f;
+  G->Dw = iend < iimg ? iend : iimg;
+  if (f > 1) {
+    // every CTA column band must fit its interior + ring-variant columns in 256 * ipt work items
+    const int ci = plane_ci(f);
+    const int variants = 2 * (ci / G->Sf + 2);
+    if ((ci + variants) * 3 > 256 * plane_ipt(f)) return false;
+  }
+  return G->ncy > 0 && G->Dh > 0 && G->Dw > 0;
+}
+
+static size_t fused_plane_bytes(const FusedGeom& G, int v, int h) {
+  const size_t rows = v == 0 ? (size_t)G.Dh : (size_t)G.ny;
+  const size_t cols = h == 0 ? (size_t)G.Dw : (size_t)G.nx;
+  return align_up(rows * cols * 3, 256);
+}
+
+static size_t fused_workspace_bytes_impl(const ScanParams& p) {
+  FusedGeom G;
+  if (!fused_geometry(p, &G)) return 0;
+  size_t b = 2 * align_up((size_t)G.ncx * G.ncy * 4, 256);
+  if (G.f > 1)
+    for (int v = 0; v < 3; v++)
+      for (int h = 0; h < 3; h++) b += fused_plane_bytes(G, v, h);
+  return b;
+}
+
+// ------------------------------------------------------------------------------------------
+// pass A1: per-cell byte sums and lesion votes (32-row bands, one warp per row)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_cell_stats(ScanParams p, FusedGeom G) {
+  const int cx = blockIdx.x;
+  const int r0 = G.cy0 * G.g + blockIdx.y * 32;
+  if (r0 >= p.H) return;
+  const int cyl = r0 / G.g - G.cy0;
+  const int r1 = min(min(r0 + 32, p.H), (G.cy0 + G.ncy) * G.g);
+  const int xb = cx * G.g, xe = min(p.W, xb + G.g);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint32_t s = 0, any = 0;
+  for (int r = r0 + warp; r < r1; r += 8) {
+    s += warp_bytes_sum(p.rgb, (int64_t)r * p.pitch + (int64_t)xb * 3, (xe - xb) * 3, 0, lane);
+    if (p.mask) any |= warp_bytes_any(p.mask, (int64_t)r * p.mask_pitch + xb, xe - xb, lane);
+  }
+  for (int o = 16; o; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    any |= __shfl_xor_sync(0xffffffffu, any, o);
+  }
+  __shared__ uint32_t sh_s[8], sh_a[8];
+  if (lane == 0) sh_s[warp] = s, sh_a[warp] = any;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t tot = 0, a = 0;
+    for (int w = 0; w < 8; w++) tot += sh_s[w], a |= sh_a[w];
+    atomicAdd(&G.cell_sum[(size_t)cyl * G.ncx + cx], tot);  // cell total <= 1792^2*3*255 < 2^32
+    if (a) atomicOr(&G.cell_any[(size_t)cyl * G.ncx + cx], 1u);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// per-candidate flags from the cell grid
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_patch_flags(ScanParams p, FusedGeom G, uint8_t* __restrict__ flags, int n_cand) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n_cand) return;
+  const int ix = idx / p.ny, iyl = idx - ix * p.ny;
+  const int x = ix * p.S, y = (p.iy_begin + iyl) * p.S;
+  const int pw = min(p.P, p.W - x), ph = min(p.P, p.H - y);
+  const int cxa = x / G.g, cya = y / G.g - G.cy0, n = p.P / G.g;
+  unsigned long long tot = 0;
+  uint32_t a = 0;
+  for (int dy = 0; dy < n && cya + dy < G.ncy; dy++)
+    for (int dx = 0; dx < n && cxa + dx < G.ncx; dx++) {
+      tot += G.cell_sum[(size_t)(cya + dy) * G.ncx + cxa + dx];
+      a |= G.cell_any[(size_t)(cya + dy) * G.ncx + cxa + dx];
+    }
+  tot += 255ull * 3ull * ((unsigned long long)p.P * p.P - (unsigned long long)pw * ph);
+  const unsigned long long limit = 240ull * 3ull * (unsigned long long)p.P * p.P;
+  flags[idx] = (tot <= limit ? 1 : 0) | (a ? 2 : 0);
+}
+
+// ------------------------------------------------------------------------------------------
+// pass A2: globally resampled level D + ring-variant planes
+//   CTA = 512 x 224 image pixels (+ f-pixel halo) -> (512/f) x (224/f) D pixels.  Image rows stream
+//   through a 3-stage cp.async ring of 8 rows; each thread owns up to IPT (column, channel) items and
+//   keeps the vertical accumulators of the two D rows an image row contributes to in registers.
+// ------------------------------------------------------------------------------------------
+constexpr int kPlaneG = 8;        // image rows per pipeline stage
+constexpr int kPlaneStages = 3;
+constexpr int kPlaneFront = 16;   // front pad so (unused) taps left of pixel 0 stay inside the buffer
+
+__host__ __device__ constexpr int plane_rowcap(int f) { return ((512 + f) * 3 + kPlaneFront + 16 + 16 + 15) / 16 * 16; }
+
+__device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int F>
+__global__ void __launch_bounds__(256) k_downsample_planes(ScanParams p, FusedGeom G) {
+  constexpr int CI = plane_ci(F), RJ = plane_rj(F), IPT = plane_ipt(F), ROWCAP = plane_rowcap(F);
+  constexpr int NI = 2 * F, NE = 3 * F / 2, HALF = F / 2;
+  constexpr int SHIFT = F == 8 ? 7 : (F == 4 ? 5 : 3);  // interior weights are (2m+1) / 2^SHIFT exactly
+  extern __shared__ __align__(16) uint8_t sm[];
+  uint8_t* rows = sm;                                                       // [stages][G][ROWCAP]
+  int* col_I = reinterpret_cast<int*>(sm + kPlaneStages * kPlaneG * ROWCAP);  // D column of each work column
+  int* col_kind = col_I + (CI + 2 * (CI / 4 + 2));                          // 0 interior, 1 left, 2 right
+  __shared__ int s_ncols;
+
+  const int I0 = blockIdx.x * CI;
+  const int Ja0 = G.Jbase + blockIdx.y * RJ;                // first D row owned by this CTA
+  const int Ja1 = min(Ja0 + RJ, G.Jbase + G.Dh);
+  const int Ib1 = min(I0 + CI, G.Dw);
+  const int tid = threadIdx.x;
+  const CoeffSet& cs = c_coef[G.lf];
+
+  // ---- work columns: interior columns of the band, then the ring-variant columns inside it ----
+  if (tid == 0) {
+    int n = 0;
+    for (int I = I0; I < Ib1; I++) col_I[n] = I, col_kind[n++] = 0;
+    for (int I = I0; I < Ib1; I++) {
+      if (I % G.Sf == 0 && I / G.Sf < G.nx) col_I[n] = I, col_kind[n++] = 1;
+      if (I >= OUT - 1 && (I - (OUT - 1)) % G.Sf == 0 && (I - (OUT - 1)) / G.Sf < G.nx) col_I[n] = I, col_kind[n++] = 2;
+    }
+    s_ncols = n;
+  }
+  __syncthreads();
+  const int ncols = s_ncols;
+  const int nitems = ncols * 3;
+
+  // ---- image window of this CTA ----
+  const int rfirst = F * Ja0 - HALF;                       // may be < 0 for the first band (rows unused)
+  const int rlast = F * Ja1 + HALF;                        // exclusive
+  const int px0 = F * I0 - HALF;                           // leftmost pixel any tap may touch
+  const int px0c = max(px0, 0);
+  const int px1c = min(p.W, F * Ib1 + HALF);               // exclusive, clamped to the image
+  const int px1 = F * Ib1 + HALF;
+  const int nbytes = (px1c - px0c) * 3;
+  const int64_t img_bytes = (int64_t)p.H * p.pitch;
+  const int nstage_total = (rlast - rfirst + kPlaneG - 1) / kPlaneG;
+
+  auto issue_stage = [&](int st) {
+    uint8_t* dst_stage = rows + (st % kPlaneStages) * kPlaneG * ROWCAP;
+    for (int rr = 0; rr < kPlaneG; rr++) {
+      const int r = rfirst + st * kPlaneG + rr;
+      if (r < 0 || r >= p.H || r >= rlast || nbytes <= 0) continue;
+      const int64_t start = (int64_t)r * p.pitch + (int64_t)px0c * 3;
+      const int64_t a0 = start & ~int64_t(15);
+      uint8_t* dst = dst_stage + rr * ROWCAP + kPlaneFront;  // dst[k] <-> global byte a0 + k
+      for (int64_t a = a0 + tid * 16; a < start + nbytes; a += 256 * 16) {
+        if (a + 16 <= img_bytes) {
+          cp_async_16(dst + (a - a0), p.rgb + a);
+        } else {
+          for (int b = 0; b < 16 && a + b < img_bytes; b++) dst[a - a0 + b] = p.rgb[a + b];
+        }
+      }
+    }
+    cp_async_commit();
+  };
+
+  // per-item state
+  int A_int[IPT], A_top[IPT], A_bot[IPT], B_int[IPT], B_top[IPT], B_bot[IPT];
+#pragma unroll
+  for (int q = 0; q < IPT; q++) A_int[q] = A_top[q] = A_bot[q] = B_int[q] = B_top[q] = B_bot[q] = 0;
+
+  for (int st = 0; st < kPlaneStages - 1 && st < nstage_total; st++) issue_stage(st);
+  for (int st = 0; st < nstage_total; st++) {
+    if (st + kPlaneStages - 1 < nstage_total) {
+      issue_stage(st + kPlaneStages - 1);
+      cp_async_wait<kPlaneStages - 1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    uint8_t* stage = rows + (st % kPlaneStages) * kPlaneG * ROWCAP;
+    // white fill: rows outside the image, and pixels right of the image edge
+    for (int rr = 0; rr < kPlaneG; rr++) {
+      const int r = rfirst + st * kPlaneG + rr;
+      if (r >= rlast) break;
+      uint8_t* rowp = stage + rr * ROWCAP;
+      const int phase = (int)((((int64_t)(r < 0 ? 0 : r) * p.pitch + (int64_t)px0c * 3)) & 15);
+      if (r < 0 || r >= p.H) {
+        for (int k = tid; k < ROWCAP; k += 256) rowp[k] = 255;
+      } else if (px1 > px1c) {
+        for (int k = nbytes + tid; k < (px1 - px0c) * 3; k += 256) rowp[kPlaneFront + phase + k] = 255;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < IPT; q++) {
+      const int e = tid + q * 256;
+      if (e >= nitems) continue;
+      const int c = e / ncols, col = e - c * ncols;
+      const int I = col_I[col], kind = col_kind[col];
+      for (int rr = 0; rr < kPlaneG; rr++) {
+        const int r = rfirst + st * kPlaneG + rr;
+        if (r >= rlast) break;
+        const uint8_t* rowp = stage + rr * ROWCAP;
+        const int phase = (int)((((int64_t)((r < 0 || r >= p.H) ? 0 : r) * p.pitch + (int64_t)px0c * 3)) & 15);
+        // byte k of the logical row (pixel px0c + k/3) sits at rowp[kPlaneFront + phase + k]
+        const uint8_t* pix = rowp + kPlaneFront + ((r < 0 || r >= p.H) ? 0 : phase) + c;
+        int h;
+        if (kind == 0) {
+          const int b0 = (F * I - HALF - px0c) * 3;  // may be negative for I == 0 (value unused; stays in the front pad)
+          int T = 0;
+#pragma unroll
+          for (int t = 0; t < NI; t++) T += (t < F ? 2 * t + 1 : 2 * (NI - 1 - t) + 1) * (int)pix[b0 + 3 * t];
+          h = (T + (1 << (SHIFT - 1))) >> SHIFT;
+        } else {
+          const int b0 = (kind == 1 ? F * I - px0c : F * I - HALF - px0c) * 3;
+          const int32_t* kh = kind == 1 ? cs.left : cs.right;
+          int acc = 1 << (kPrecisionBits - 1);
+#pragma unroll
+          for (int t = 0; t < NE; t++) acc += kh[t] * (int)pix[b0 + 3 * t];
+          h = min(max(acc >> kPrecisionBits, 0), 255);
+        }
+        // ---- vertical accumulation: image row r feeds D rows Jb (tap tb) and Jb-1 (tap tb+F) ----
+        const int d = r + HALF;
+        const int Jb = d / F, tb = d - Jb * F;
+        B_int[q] += (2 * tb + 1) * h;
+        A_int[q] += (2 * (F - 1 - tb) + 1) * h;
+        B_bot[q] += cs.right[tb] * h;
+        if (tb < HALF) A_bot[q] += cs.right[tb + F] * h;
+        if (tb >= HALF) B_top[q] += cs.left[tb - HALF] * h;
+        A_top[q] += cs.left[tb + HALF] * h;
+        if (tb == F - 1) {
+          const int J = Jb - 1;
+          if (J >= Ja0 && J < Ja1) {
+            const int hk = kind;
+            const int ixv = kind == 1 ? I / G.Sf : (kind == 2 ? (I - (OUT - 1)) / G.Sf : 0);
+            const size_t ccol = hk == 0 ? (size_t)I : (size_t)ixv;
+            const size_t cw = hk == 0 ? (size_t)G.Dw : (size_t)G.nx;
+            G.plane[0][hk][((size_t)(J - G.Jbase) * cw + ccol) * 3 + c] = (uint8_t)((A_int[q] + (1 << (SHIFT - 1))) >> SHIFT);
+            if (J % G.Sf == 0) {
+              const int iy = J / G.Sf - G.iy_begin;
+              if (iy >= 0 && iy < G.ny)
+                G.plane[1][hk][((size_t)iy * cw + ccol) * 3 + c] =
+                    (uint8_t)min(max((A_top[q] + (1 << (kPrecisionBits - 1))) >> kPrecisionBits, 0), 255);
+            }
+            if (J >= OUT - 1 && (J - (OUT - 1)) % G.Sf == 0) {
+              const int iy = (J - (OUT - 1)) / G.Sf - G.iy_begin;
+              if (iy >= 0 && iy < G.ny)
+                G.plane[2][hk][((size_t)iy * cw + ccol) * 3 + c] =
+                    (uint8_t)min(max((A_bot[q] + (1 << (kPrecisionBits - 1))) >> kPrecisionBits, 0), 255);
+            }
+          }
+          A_int[q] = B_int[q], A_top[q] = B_top[q], A_bot[q] = B_bot[q];
+          B_int[q] = B_top[q] = B_bot[q] = 0;
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// pass B: gather the 224 x 224 crop of every survivor from the planes (or the image when f == 1)
+//   grid (survivor slot, 112 row pairs); thread X of a row pair produces the 2x2 output pixels
+//   (2*jp+dy, 2*X+dx) -- exactly one 32-byte space-to-depth pixel of the conv1 operand.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t fused_fetch(const ScanParams& p, const FusedGeom& G, int x, int y, int iyl, int j,
+                                                int i, int c) {
+  if (G.f == 1) {
+    const int yy = y + j, xx = x + i;
+    return (yy < p.H && xx < p.W) ? p.rgb[(int64_t)yy * p.pitch + (int64_t)xx * 3 + c] : 255u;
+  }
+  const int J = y / G.f + j - G.Jbase, I = x / G.f + i;
+  if (J >= G.Dh || I >= G.Dw) return 255u;  // window entirely in the white padding
+  const int vk = j == 0 ? 1 : (j == OUT - 1 ? 2 : 0), hk = i == 0 ? 1 : (i == OUT - 1 ? 2 : 0);
+  const size_t row = vk == 0 ? (size_t)J : (size_t)iyl;
+  const size_t cw = hk == 0 ? (size_t)G.Dw : (size_t)G.nx;
+  const size_t col = hk == 0 ? (size_t)I : (size_t)(x / p.S);
+  return G.plane[vk][hk][(row * cw + col) * 3 + c];
+}
+
+__global__ void __launch_bounds__(128) k_gather(ScanParams p, FusedGeom G, OutParams o, const int32_t* __restrict__ coords,
+                                                const int32_t* __restrict__ count, int capacity) {
+  const int slot = blockIdx.x, jp = blockIdx.y;
+  if (slot >= min(count[0], capacity)) return;
+  const int x = coords[2 * slot], y = coords[2 * slot + 1];
+  const int iyl = y / p.S - p.iy_begin;
+  const int X = threadIdx.x;
+  if (X >= OUT / 2) return;
+  uint32_t v[2][2][3];
+#pragma unroll
+  for (int dy = 0; dy < 2; dy++)
+#pragma unroll
+    for (int dx = 0; dx < 2; dx++)
+#pragma unroll
+      for (int c = 0; c < 3; c++) v[dy][dx][c] = fused_fetch(p, G, x, y, iyl, 2 * jp + dy, 2 * X + dx, c);
+  if (o.batch_u8) {
+#pragma unroll
+    for (int dy = 0; dy < 2; dy++)
+#pragma unroll
+      for (int dx = 0; dx < 2; dx++)
+#pragma unroll
+        for (int c = 0; c < 3; c++)
+          o.batch_u8[(((int64_t)slot * OUT + 2 * jp + dy) * OUT + 2 * X + dx) * 3 + c] = (uint8_t)v[dy][dx][c];
+  }
+  if (o.batch) {
+    if (o.layout == HIPAC_LAYOUT_S2D16_BF16) {
+      uint32_t w[8];
+#pragma unroll
+      for (int k = 0; k < 6; k++) {
+        const int e0 = 2 * k, e1 = 2 * k + 1;  // channel index (dy*2+dx)*3+c
+        const uint32_t lo = c_lut_bf16[v[e0 / 6][(e0 / 3) & 1][e0 % 3] * 3 + e0 % 3];
+        const uint32_t hi = c_lut_bf16[v[e1 / 6][(e1 / 3) & 1][e1 % 3] * 3 + e1 % 3];
+        w[k] = lo | (hi << 16);
+      }
+      w[6] = w[7] = 0;
+      uint4* dst = reinterpret_cast<uint4*>(o.batch + ((((int64_t)slot * (OUT / 2) + jp) * (OUT / 2) + X) << 4));
+      dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
+      dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
+    } else {
+#pragma unroll
+      for (int dy = 0; dy < 2; dy++)
+#pragma unroll
+        for (int dx = 0; dx < 2; dx++)
+#pragma unroll
+          for (int c = 0; c < 3; c++)
+            o.batch[(((int64_t)slot * OUT + 2 * jp + dy) * OUT + 2 * X + dx) * 3 + c] = c_lut_bf16[v[dy][dx][c] * 3 + c];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// host driver
+// ------------------------------------------------------------------------------------------
+template <int F>
+static int launch_planes(const ScanParams& p, const FusedGeom& G, cudaStream_t stream) {
+  constexpr int CI = plane_ci(F), RJ = plane_rj(F);
+  const size_t smem = (size_t)kPlaneStages * kPlaneG * plane_rowcap(F) + 2 * (CI + 2 * (CI / 4 + 2)) * sizeof(int);
+  static bool attr = false;
+  if (!attr) {
+    HIPAC_CHECK_CUDA(cudaFuncSetAttribute(k_downsample_planes<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = true;
+  }
+  dim3 grid((G.Dw + CI - 1) / CI, (G.Dh + RJ - 1) / RJ);
+  ProfileScope ps("downsample_planes", stream, (double)p.H * p.W * 3);
+  k_downsample_planes<F><<<grid, 256, smem, stream>>>(p, G);
+  count_launch(1);
+  return 0;
+}
+
+static int fused_scan_impl(const ScanParams& p, const OutParams& o, uint8_t* flags, int32_t* src_idx, int32_t* d_coords,
+                           uint8_t* d_labels, int32_t* d_count, int capacity, uint8_t* ws, cudaStream_t stream) {
+  FusedGeom G;
+  if (!fused_geometry(p, &G)) {
+    set_error("fused scan not applicable to this stride / patch size");
+    return -4;
+  }
+  const size_t cell_bytes = align_up((size_t)G.ncx * G.ncy * 4, 256);
+  G.cell_sum = reinterpret_cast<uint32_t*>(ws);
+  G.cell_any = reinterpret_cast<uint32_t*>(ws + cell_bytes);
+  ws += 2 * cell_bytes;
+  for (int v = 0; v < 3; v++)
+    for (int h = 0; h < 3; h++) {
+      G.plane[v][h] = G.f > 1 ? ws : nullptr;
+      if (G.f > 1) ws += fused_plane_bytes(G, v, h);
+    }
+  const int n_cand = p.nx * p.ny;
+  HIPAC_CHECK_CUDA(cudaMemsetAsync(G.cell_sum, 0, 2 * cell_bytes, stream));
+  {
+    const int rows = min(p.H, (G.cy0 + G.ncy) * G.g) - G.cy0 * G.g;
+    dim3 grid(G.ncx, (rows + 31) / 32);
+    ProfileScope ps("cell_stats", stream, (double)rows * p.W * (p.mask ? 4 : 3));
+    k_cell_stats<<<grid, 256, 0, stream>>>(p, G);
+  }
+  {
+    ProfileScope ps("patch_flags", stream, 0.0);
+    k_patch_flags<<<(n_cand + 255) / 256, 256, 0, stream>>>(p, G, flags, n_cand);
+  }
+  {
+    ProfileScope ps("compact", stream, (double)n_cand);
+    k_compact<<<1, 1024, 0, stream>>>(p, flags, n_cand, d_coords, d_labels, src_idx, d_count, capacity);
+  }
+  count_launch(3);
+  if ((o.batch_u8 || o.batch) && capacity > 0) {
+    if (G.f == 2) {
+      if (int e = launch_planes<2>(p, G, stream)) return e;
+    } else if (G.f == 4) {
+      if (int e = launch_planes<4>(p, G, stream)) return e;
+    } else if (G.f == 8) {
+      if (int e = launch_planes<8>(p, G, stream)) return e;
+    }
+    dim3 grid((unsigned)min(n_cand, capacity), OUT / 2);
+    ProfileScope ps("gather", stream, 0.0);
+    k_gather<<<grid, 128, 0, stream>>>(p, G, o, d_coords, d_count, capacity);
+    count_launch(1);
+  }
+  HIPAC_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}

@@ -27,10 +27,4 @@ struct OutParams {
   int layout;
 };
 
-// fused (read-once) path, tile_scan_fused.cu
-bool fused_available();
-size_t fused_workspace_bytes(int H, int W, int P, int S, int iy_begin, int iy_end, int mode);
-int fused_scan(const ScanParams& p, const OutParams& o, uint8_t* flags, int32_t* src_idx, int32_t* d_coords,
-               uint8_t* d_labels, int32_t* d_count, int capacity, uint8_t* ws, cudaStream_t stream);
-
 }  // namespace hipac

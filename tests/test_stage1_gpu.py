@@ -111,3 +111,26 @@ def test_pitched_input_and_errors():
         extract_patches_tensor(view, None, 3, row_range=(0, 99))
     with pytest.raises(RuntimeError):
         extract_patches_tensor(view, None, 3, capacity=1)
+
+
+@pytest.mark.parametrize("level,stride", [(0, None), (1, None), (2, None), (3, None), (0, 1792), (1, 896), (2, 448), (1, 448), (0, 32 * 8)])
+def test_fused_equals_direct_bitwise(level, stride):
+    """The read-once path and the per-patch path are two implementations of the same function."""
+    rng = np.random.default_rng(level + 17)
+    h, w = 2600 + 37 * level, 3100 + 11 * level
+    img = rng.integers(150, 256, size=(h, w, 3), dtype=np.uint8)
+    img[300:1900, 500:2500] = rng.integers(0, 256, size=(1600, 2000, 3), dtype=np.uint8)
+    mask = np.zeros((h, w), np.uint8)
+    mask[700:720, 900:2000] = 7
+    a = _run(img, mask, level, stride, mode="direct", layout="s2d16")
+    b = _run(img, mask, level, stride, mode="fused", layout="s2d16")
+    assert a.candidates == b.candidates and len(a) == len(b) > 0
+    assert torch.equal(a.coords, b.coords) and torch.equal(a.labels, b.labels)
+    assert torch.equal(a.images_u8, b.images_u8)
+    assert torch.equal(a.batch.view(torch.int16), b.batch.view(torch.int16))
+
+
+def test_fused_mode_rejects_unaligned_stride():
+    img = np.full((1000, 1000, 3), 100, np.uint8)
+    with pytest.raises(RuntimeError, match="fused scan needs"):
+        _run(img, None, 1, 300, mode="fused")
