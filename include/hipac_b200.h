@@ -29,7 +29,10 @@ extern "C" {
 
 /* batch layouts written by hipac_tile_scan / consumed by hipac_resnet18_forward */
 #define HIPAC_LAYOUT_NHWC3_BF16 1 /* bf16 [N,224,224,3], (u8/255-mean)/std, the reference's tensor (src/main.py:815-816) in NHWC */
-#define HIPAC_LAYOUT_S2D16_BF16 2 /* bf16 [N,112,112,16]: 2x2 space-to-depth of the above, ch=(dy*2+dx)*3+c, 12..15 zero (conv1 operand) */
+#define HIPAC_LAYOUT_S2D16_BF16 2 /* bf16 [N,112,115,16]: 2x2 space-to-depth of the above, ch=(dy*2+dx)*3+c, 12..15 zero; column X of the
+                                    image sits at index X+2, columns 0,1,114 are zero (conv1's W padding made explicit so that the four
+                                    W-taps of a filter row are one contiguous 128-byte TMA row) */
+#define HIPAC_S2D16_WIDTH 115
 
 /* stage-1 algorithm selector */
 #define HIPAC_SCAN_AUTO   0 /* fused read-once path when stride %% (P/224) == 0, else direct */
@@ -115,6 +118,12 @@ int hipac_resnet18_conv_layer(const void* d_packed, int num_classes, int layer,
 /* Number of kernel launches issued by this library on the calling thread since the last reset
  * (bench.py's "gpu_launches"). */
 long long hipac_launch_count(int reset);
+
+/* Test hook for the shifted-descriptor mechanism of the row-tile conv kernels:
+ * D[m][n] = sum_k A[m + shift_rows][k] * B[n][k] (m < 128, n < 64) with A [256][K], B [64][K] bf16,
+ * K = 64 (swizzle_bytes = 128) or 16 (swizzle_bytes = 32); A and B are TMA-loaded whole, the UMMA A
+ * descriptor starts shift_rows rows into the tile. */
+int hipac_debug_umma_shift(const void* d_A, const void* d_B, float* d_D, int shift_rows, int swizzle_bytes, void* stream);
 
 /* Optional per-kernel profiler (calling thread): when enabled every kernel launch of the library is
  * bracketed by CUDA events on its stream.  hipac_profile_report synchronises them, writes one line per

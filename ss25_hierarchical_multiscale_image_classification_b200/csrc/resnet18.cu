@@ -23,7 +23,7 @@ namespace hipac {
 struct ConvParams {
   int M_total;       // images * hout * wout (GEMM M)
   int hw_out, wout;  // hout*wout, wout
-  int stride, pad;
+  int stride, pad_w, pad_h;
   int kw;            // filter width (taps per filter row)
   int kc_blocks;     // 64-channel blocks per tap (cin / 64)
   int num_kb;        // k-blocks per tile
@@ -36,7 +36,8 @@ struct ConvParams {
 };
 
 constexpr int kBM = 128;
-constexpr int kABytes = kBM * 128;  // 128 rows x 64 bf16 (or 4 taps x 128 rows x 16 bf16 for conv1)
+constexpr int kS2dW = HIPAC_S2D16_WIDTH;  // 112 + 3 explicit zero columns (2 left, 1 right)
+constexpr int kABytes = kBM * 128;  // 128 rows x 64 bf16
 constexpr int kConvThreads = 192;   // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
 
 template <int BN>
@@ -48,7 +49,7 @@ struct ConvCfg {
   static constexpr int kSmemBytes = kStages * kStage + 1024 /*alignment slack*/ + 256 /*barriers*/;
 };
 
-template <int BN, bool CONV1>
+template <int BN>
 __global__ void __launch_bounds__(kConvThreads, 1)
 k_conv_umma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvParams p) {
   using Cfg = ConvCfg<BN>;
@@ -88,21 +89,15 @@ k_conv_umma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const int m0 = m_tile * kBM;
         const int img = m0 / p.hw_out, rem = m0 - img * p.hw_out;
         const int p0 = rem / p.wout, q0 = rem - p0 * p.wout;
-        const int cw = q0 * p.stride - p.pad, ch = p0 * p.stride - p.pad;
+        const int cw = q0 * p.stride - p.pad_w, ch = p0 * p.stride - p.pad_h;
         for (int kb = 0; kb < p.num_kb; kb++) {
           ptx::mbar_wait(&empty[stage], phase ^ 1);
           ptx::mbar_arrive_expect_tx(&full[stage], Cfg::kStage);
           uint8_t* a_dst = base + stage * Cfg::kStage;
           uint8_t* b_dst = a_dst + kABytes;
-          if (CONV1) {
-            // k-block = one row `a` of the 4x4 space-to-depth filter: 4 taps of 16 channels each
-            for (int b = 0; b < 4; b++)
-              ptx::tma_load_im2col_4d(a_dst + b * 4096, &tmA, &full[stage], 0, cw, ch, img, (uint16_t)b, (uint16_t)kb);
-          } else {
-            const int tap = kb / p.kc_blocks, kc = kb - tap * p.kc_blocks;
-            const int r = tap / p.kw, s = tap - r * p.kw;
-            ptx::tma_load_im2col_4d(a_dst, &tmA, &full[stage], kc * 64, cw, ch, img, (uint16_t)s, (uint16_t)r);
-          }
+          const int tap = kb / p.kc_blocks, kc = kb - tap * p.kc_blocks;
+          const int r = tap / p.kw, s = tap - r * p.kw;
+          ptx::tma_load_im2col_4d(a_dst, &tmA, &full[stage], kc * 64, cw, ch, img, (uint16_t)s, (uint16_t)r);
           ptx::tma_load_2d(b_dst, &tmB, &full[stage], kb * 64, n_tile * BN);
           if (++stage == Cfg::kStages) stage = 0, phase ^= 1;
         }
@@ -125,7 +120,7 @@ k_conv_umma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           const uint32_t b_addr = a_addr + kABytes;
 #pragma unroll
           for (int k = 0; k < 4; k++) {  // 4 x (K = 16) per 64-wide k-block
-            const uint64_t adesc = CONV1 ? ptx::make_smem_desc(a_addr + k * 4096, 32) : ptx::make_smem_desc(a_addr + k * 32, 128);
+            const uint64_t adesc = ptx::make_smem_desc(a_addr + k * 32, 128);
             const uint64_t bdesc = ptx::make_smem_desc(b_addr + k * 32, 128);
             ptx::umma_bf16(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
           }
@@ -267,20 +262,21 @@ __global__ void __launch_bounds__(256) k_avgpool_fc(const __nv_bfloat16* __restr
   }
 }
 
-// bf16 NHWC3 [n,224,224,3] -> S2D16 [n,112,112,16] (used when the caller hands the plain layout).
+// bf16 NHWC3 [n,224,224,3] -> S2D16 [n,112,115,16] (used when the caller hands the plain layout).
 __global__ void __launch_bounds__(256) k_pack_s2d16(const uint16_t* __restrict__ in, uint16_t* __restrict__ out, int n_img) {
-  const int64_t total = (int64_t)n_img * 112 * 112;
+  const int64_t total = (int64_t)n_img * 112 * kS2dW;
   for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
-    const int X = (int)(t % 112);
-    const int Y = (int)((t / 112) % 112);
-    const int64_t img = t / (112 * 112);
+    const int X = (int)(t % kS2dW) - 2;
+    const int Y = (int)((t / kS2dW) % 112);
+    const int64_t img = t / (112 * kS2dW);
     uint16_t v[16];
 #pragma unroll
     for (int dy = 0; dy < 2; dy++)
 #pragma unroll
       for (int dx = 0; dx < 2; dx++)
 #pragma unroll
-        for (int c = 0; c < 3; c++) v[(dy * 2 + dx) * 3 + c] = in[((img * 224 + 2 * Y + dy) * 224 + 2 * X + dx) * 3 + c];
+        for (int c = 0; c < 3; c++)
+          v[(dy * 2 + dx) * 3 + c] = (X >= 0 && X < 112) ? in[((img * 224 + 2 * Y + dy) * 224 + 2 * X + dx) * 3 + c] : (uint16_t)0;
     v[12] = v[13] = v[14] = v[15] = 0;
     uint4* dst = reinterpret_cast<uint4*>(out + t * 16);
     dst[0] = *reinterpret_cast<uint4*>(&v[0]);
@@ -318,15 +314,21 @@ static int init_driver_api() {
 }
 
 // NHWC activation tensor [n][h][w][c] (bf16) as an im2col map: box = 128 output pixels x `chan_box` channels.
-static int make_im2col_map(CUtensorMap* map, const void* ptr, int n, int h, int w, int c, int chan_box, int ksize, int stride,
-                           int pad_lo, int pad_hi, CUtensorMapSwizzle swz) {
-  cuuint64_t dims[4] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
-  cuuint64_t strides[3] = {(cuuint64_t)c * 2, (cuuint64_t)w * c * 2, (cuuint64_t)h * w * c * 2};
-  int lower[2] = {-pad_lo, -pad_lo};
-  int upper[2] = {pad_hi - (ksize - 1), pad_hi - (ksize - 1)};
-  cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
+struct Im2colDesc {
+  int n, h, w, c;                 // logical NHWC extents seen by TMA
+  int64_t pix_stride, row_stride, img_stride;  // bytes
+  int kh, kw, stride;             // filter extent and traversal stride
+  int pad_w_lo, pad_w_hi, pad_h_lo, pad_h_hi;
+};
+static int make_im2col_map(CUtensorMap* map, const void* ptr, const Im2colDesc& d) {
+  cuuint64_t dims[4] = {(cuuint64_t)d.c, (cuuint64_t)d.w, (cuuint64_t)d.h, (cuuint64_t)d.n};
+  cuuint64_t strides[3] = {(cuuint64_t)d.pix_stride, (cuuint64_t)d.row_stride, (cuuint64_t)d.img_stride};
+  int lower[2] = {-d.pad_w_lo, -d.pad_h_lo};
+  int upper[2] = {d.pad_w_hi - (d.kw - 1), d.pad_h_hi - (d.kh - 1)};
+  cuuint32_t estr[4] = {1, (cuuint32_t)d.stride, (cuuint32_t)d.stride, 1};
+  const int n = d.n, h = d.h, w = d.w, c = d.c;
   CUresult r = g_encode_im2col(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, lower, upper,
-                               (cuuint32_t)chan_box, (cuuint32_t)kBM, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+                               64u, (cuuint32_t)kBM, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                                CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeIm2col failed with CUresult " + std::to_string((int)r));
@@ -356,20 +358,20 @@ static int make_weight_map(CUtensorMap* map, const void* ptr, int cout, int K, i
   return 0;
 }
 
-template <int BN, bool CONV1>
+template <int BN>
 static int launch_conv_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvParams& p, cudaStream_t stream,
                          const char* name, double flops) {
   using Cfg = ConvCfg<BN>;
   static bool attr_set = false;
   if (!attr_set) {
-    HIPAC_CHECK_CUDA(cudaFuncSetAttribute(k_conv_umma<BN, CONV1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    HIPAC_CHECK_CUDA(cudaFuncSetAttribute(k_conv_umma<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_set = true;
   }
   const int tiles = p.num_m_tiles * p.num_n_tiles;
   const int grid = tiles < g_num_sms ? tiles : g_num_sms;
   {
     ProfileScope ps(name, stream, flops);
-    k_conv_umma<BN, CONV1><<<grid, kConvThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, p);
+    k_conv_umma<BN><<<grid, kConvThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, p);
   }
   count_launch(1);
   HIPAC_CHECK_CUDA(cudaGetLastError());
@@ -395,21 +397,25 @@ static int run_conv(const uint8_t* d_packed, const PackedLayout& L, int layer, c
   CUtensorMap tmA, tmB;
   if (int e = make_weight_map(&tmB, d_packed + L.w_off[layer], cs.cout, K, bn)) return e;
   if (layer == 0) {
-    // 7x7/s2/p3 over 3 channels == 4x4/s1 over the 2x2 space-to-depth image (16 ch), pad 2 before / 1 after
-    p.stride = 1, p.pad = 2, p.kw = 4, p.kc_blocks = 1, p.num_kb = 4;
-    if (int e = make_im2col_map(&tmA, in, n, 112, 112, 16, 16, 4, 1, 2, 1, CU_TENSOR_MAP_SWIZZLE_32B)) return e;
-    return launch_conv_t<64, true>(tmA, tmB, p, stream, "conv1_7x7s2_c64", 2.0 * p.M_total * 64 * 147);
+    // 7x7/s2/p3 over 3 channels == 4x4/s1 over the 2x2 space-to-depth image (16 ch), pad 2 before / 1 after.
+    // The S2D16 batch stores the W padding explicitly ([n][112][115][16], zero columns 0,1,114), so the four
+    // W-taps of one filter row are 64 CONTIGUOUS bf16: the conv is a 4x1 filter over a 64-"channel" view whose
+    // pixel stride (32 B) is smaller than its channel extent (128 B).  H padding stays TMA zero fill.
+    p.stride = 1, p.pad_w = 0, p.pad_h = 2, p.kw = 1, p.kc_blocks = 1, p.num_kb = 4;
+    Im2colDesc d{n, 112, 112, 64, 32, (int64_t)kS2dW * 32, (int64_t)112 * kS2dW * 32, 4, 1, 1, 0, 0, 2, 1};
+    if (int e = make_im2col_map(&tmA, in, d)) return e;
+    return launch_conv_t<64>(tmA, tmB, p, stream, "conv1_7x7s2_c64", 2.0 * p.M_total * 64 * 147);
   }
-  p.stride = cs.stride, p.pad = cs.pad, p.kw = cs.k, p.kc_blocks = cs.cin / 64, p.num_kb = cs.k * cs.k * p.kc_blocks;
-  if (int e = make_im2col_map(&tmA, in, n, cs.hin, cs.hin, cs.cin, 64, cs.k, cs.stride, cs.pad, cs.pad, CU_TENSOR_MAP_SWIZZLE_128B))
-    return e;
+  p.stride = cs.stride, p.pad_w = p.pad_h = cs.pad, p.kw = cs.k, p.kc_blocks = cs.cin / 64, p.num_kb = cs.k * cs.k * p.kc_blocks;
+  Im2colDesc d{n, cs.hin, cs.hin, cs.cin, (int64_t)cs.cin * 2, (int64_t)cs.hin * cs.cin * 2, (int64_t)cs.hin * cs.hin * cs.cin * 2,
+               cs.k, cs.k, cs.stride, cs.pad, cs.pad, cs.pad, cs.pad};
+  if (int e = make_im2col_map(&tmA, in, d)) return e;
   static const char* kNames[4][2] = {{"conv3x3_c64", "conv1x1_c64"}, {"conv3x3_c128", "conv1x1_c128"},
                                      {"conv3x3_c256", "conv1x1_c256"}, {"conv3x3_c512", "conv1x1_c512"}};
   const int gi = cs.cout == 64 ? 0 : cs.cout == 128 ? 1 : cs.cout == 256 ? 2 : 3;
   const char* name = kNames[gi][cs.k == 1 ? 1 : 0];
   const double flops = 2.0 * p.M_total * cs.cout * K;
-  return bn == 128 ? launch_conv_t<128, false>(tmA, tmB, p, stream, name, flops)
-                   : launch_conv_t<64, false>(tmA, tmB, p, stream, name, flops);
+  return bn == 128 ? launch_conv_t<128>(tmA, tmB, p, stream, name, flops) : launch_conv_t<64>(tmA, tmB, p, stream, name, flops);
 }
 
 static uint16_t host_bf16(float f) {
@@ -423,10 +429,10 @@ static uint16_t host_bf16(float f) {
 // per-chunk activation buffers (bf16 NHWC), sizes per patch
 constexpr size_t kC1Bytes = (size_t)112 * 112 * 64 * 2;  // conv1 output
 constexpr size_t kActBytes = (size_t)56 * 56 * 64 * 2;   // largest post-pool activation
-constexpr size_t kS2dBytes = (size_t)112 * 112 * 16 * 2;
+constexpr size_t kS2dBytes = (size_t)112 * kS2dW * 16 * 2;
 
 static int clamp_chunk(int chunk, int n) {
-  if (chunk <= 0) chunk = 128;
+  if (chunk <= 0) chunk = 4096;
   if (chunk > n) chunk = n;
   return chunk < 1 ? 1 : chunk;
 }

@@ -13,6 +13,7 @@ namespace hipac {
 // ------------------------------------------------------------------------------------------
 __constant__ CoeffSet c_coef[4];          // index log2(scale); [0] unused
 __constant__ uint16_t c_lut_bf16[768];    // [v][c] -> bf16 bits of (v/255 - mean_c)/std_c
+__device__ uint16_t g_lut_bf16[768];      // same table in global memory (gathered with divergent indices)
 
 static const float kMean[3] = {0.485f, 0.456f, 0.406f};  // reference src/main.py:816
 static const float kStd[3] = {0.229f, 0.224f, 0.225f};
@@ -52,6 +53,7 @@ static int upload_constants(cudaStream_t stream) {
   host_normalize_lut_bf16(h_lut);
   HIPAC_CHECK_CUDA(cudaMemcpyToSymbolAsync(c_coef, h_coef, sizeof(h_coef), 0, cudaMemcpyHostToDevice, stream));
   HIPAC_CHECK_CUDA(cudaMemcpyToSymbolAsync(c_lut_bf16, h_lut, sizeof(h_lut), 0, cudaMemcpyHostToDevice, stream));
+  HIPAC_CHECK_CUDA(cudaMemcpyToSymbolAsync(g_lut_bf16, h_lut, sizeof(h_lut), 0, cudaMemcpyHostToDevice, stream));
   HIPAC_CHECK_CUDA(cudaStreamSynchronize(stream));
   if (dev < 64) done[dev] = true;
   return 0;
@@ -183,16 +185,18 @@ __device__ __forceinline__ void write_output(const OutParams& o, int slot, int j
     if (o.layout == HIPAC_LAYOUT_NHWC3_BF16) {
       o.batch[(((int64_t)slot * OUT + j) * OUT + i) * 3 + c] = b;
     } else {
-      o.batch[((((int64_t)slot * (OUT / 2) + (j >> 1)) * (OUT / 2) + (i >> 1)) << 4) + ((j & 1) * 2 + (i & 1)) * 3 + c] = b;
+      o.batch[((((int64_t)slot * (OUT / 2) + (j >> 1)) * HIPAC_S2D16_WIDTH + (i >> 1) + 2) << 4) + ((j & 1) * 2 + (i & 1)) * 3 + c] = b;
     }
   }
 }
 
 __device__ __forceinline__ void write_s2d_pad(const OutParams& o, int slot, int j) {
   if (o.batch && o.layout == HIPAC_LAYOUT_S2D16_BF16 && (j & 1)) {
-    for (int X = threadIdx.x; X < OUT / 2; X += blockDim.x) {
-      uint2* q = reinterpret_cast<uint2*>(o.batch + ((((int64_t)slot * (OUT / 2) + (j >> 1)) * (OUT / 2) + X) << 4) + 12);
-      *q = make_uint2(0u, 0u);
+    uint16_t* row = o.batch + (((int64_t)slot * (OUT / 2) + (j >> 1)) * HIPAC_S2D16_WIDTH << 4);
+    for (int X = threadIdx.x; X < OUT / 2; X += blockDim.x) *reinterpret_cast<uint2*>(row + ((X + 2) << 4) + 12) = make_uint2(0u, 0u);
+    if (threadIdx.x < 3) {  // explicit zero columns 0, 1 and 114
+      uint4* q = reinterpret_cast<uint4*>(row + ((threadIdx.x < 2 ? threadIdx.x : HIPAC_S2D16_WIDTH - 1) << 4));
+      q[0] = q[1] = make_uint4(0u, 0u, 0u, 0u);
     }
   }
 }

@@ -319,8 +319,9 @@ __global__ void __launch_bounds__(256) k_downsample_planes(ScanParams p, FusedGe
 
 // ------------------------------------------------------------------------------------------
 // pass B: gather the 224 x 224 crop of every survivor from the planes (or the image when f == 1)
-//   grid (survivor slot, 112 row pairs); thread X of a row pair produces the 2x2 output pixels
-//   (2*jp+dy, 2*X+dx) -- exactly one 32-byte space-to-depth pixel of the conv1 operand.
+//   grid (survivor slot, 14 groups of 8 row pairs); the 16 plane rows are staged in shared memory, then
+//   thread X of a row pair produces the 2x2 output pixels (2*jp+dy, 2*X+dx) -- exactly one 32-byte
+//   space-to-depth pixel of the conv1 operand.
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t fused_fetch(const ScanParams& p, const FusedGeom& G, int x, int y, int iyl, int j,
                                                 int i, int c) {
@@ -337,52 +338,65 @@ __device__ __forceinline__ uint32_t fused_fetch(const ScanParams& p, const Fused
   return G.plane[vk][hk][(row * cw + col) * 3 + c];
 }
 
+constexpr int kGatherPairs = 8;  // output row pairs per CTA (112 = 14 * 8)
+
 __global__ void __launch_bounds__(128) k_gather(ScanParams p, FusedGeom G, OutParams o, const int32_t* __restrict__ coords,
                                                 const int32_t* __restrict__ count, int capacity) {
-  const int slot = blockIdx.x, jp = blockIdx.y;
+  const int slot = blockIdx.x, jp0 = blockIdx.y * kGatherPairs;
   if (slot >= min(count[0], capacity)) return;
+  __shared__ __align__(16) uint8_t rowbuf[2 * kGatherPairs][OUT * 3];
+  __shared__ uint16_t lut[768];
   const int x = coords[2 * slot], y = coords[2 * slot + 1];
   const int iyl = y / p.S - p.iy_begin;
-  const int X = threadIdx.x;
-  if (X >= OUT / 2) return;
-  uint32_t v[2][2][3];
-#pragma unroll
-  for (int dy = 0; dy < 2; dy++)
-#pragma unroll
-    for (int dx = 0; dx < 2; dx++)
-#pragma unroll
-      for (int c = 0; c < 3; c++) v[dy][dx][c] = fused_fetch(p, G, x, y, iyl, 2 * jp + dy, 2 * X + dx, c);
-  if (o.batch_u8) {
-#pragma unroll
-    for (int dy = 0; dy < 2; dy++)
-#pragma unroll
-      for (int dx = 0; dx < 2; dx++)
-#pragma unroll
-        for (int c = 0; c < 3; c++)
-          o.batch_u8[(((int64_t)slot * OUT + 2 * jp + dy) * OUT + 2 * X + dx) * 3 + c] = (uint8_t)v[dy][dx][c];
+  const int tid = threadIdx.x;
+  for (int e = tid; e < 384; e += 128) reinterpret_cast<uint32_t*>(lut)[e] = reinterpret_cast<const uint32_t*>(g_lut_bf16)[e];
+  // stage 16 output rows (672 contiguous plane bytes each) with coalesced byte loads
+  for (int e = tid; e < 2 * kGatherPairs * OUT * 3; e += 128) {
+    const int rr = e / (OUT * 3), k = e - rr * (OUT * 3);
+    const int i = k / 3, c = k - 3 * i;
+    rowbuf[rr][k] = (uint8_t)fused_fetch(p, G, x, y, iyl, 2 * jp0 + rr, i, c);
   }
-  if (o.batch) {
-    if (o.layout == HIPAC_LAYOUT_S2D16_BF16) {
+  __syncthreads();
+  const int X = tid;
+  if (o.batch_u8) {
+    for (int rr = 0; rr < 2 * kGatherPairs; rr++) {
+      uint8_t* dst = o.batch_u8 + (((int64_t)slot * OUT + 2 * jp0 + rr) * OUT) * 3;
+      for (int k = tid; k < OUT * 3; k += 128) dst[k] = rowbuf[rr][k];
+    }
+  }
+  if (!o.batch) return;
+  if (o.layout == HIPAC_LAYOUT_S2D16_BF16) {
+    if (X >= OUT / 2) {
+      // threads 112..114 write the explicit zero columns 0, 1, 114 of the padded space-to-depth rows
+      if (X < OUT / 2 + 3) {
+        const int col = X - OUT / 2 < 2 ? X - OUT / 2 : HIPAC_S2D16_WIDTH - 1;
+        for (int q = 0; q < kGatherPairs; q++) {
+          uint4* dst = reinterpret_cast<uint4*>(o.batch + ((((int64_t)slot * (OUT / 2) + jp0 + q) * HIPAC_S2D16_WIDTH + col) << 4));
+          dst[0] = dst[1] = make_uint4(0u, 0u, 0u, 0u);
+        }
+      }
+      return;
+    }
+#pragma unroll 2
+    for (int q = 0; q < kGatherPairs; q++) {
       uint32_t w[8];
 #pragma unroll
       for (int k = 0; k < 6; k++) {
-        const int e0 = 2 * k, e1 = 2 * k + 1;  // channel index (dy*2+dx)*3+c
-        const uint32_t lo = c_lut_bf16[v[e0 / 6][(e0 / 3) & 1][e0 % 3] * 3 + e0 % 3];
-        const uint32_t hi = c_lut_bf16[v[e1 / 6][(e1 / 3) & 1][e1 % 3] * 3 + e1 % 3];
-        w[k] = lo | (hi << 16);
+        // channel index ch = (dy*2+dx)*3+c of the 32-byte space-to-depth pixel; two channels per word
+        const int e0 = 2 * k, e1 = 2 * k + 1;
+        const uint32_t v0 = rowbuf[2 * q + e0 / 6][(2 * X + ((e0 / 3) & 1)) * 3 + e0 % 3];
+        const uint32_t v1 = rowbuf[2 * q + e1 / 6][(2 * X + ((e1 / 3) & 1)) * 3 + e1 % 3];
+        w[k] = (uint32_t)lut[v0 * 3 + e0 % 3] | ((uint32_t)lut[v1 * 3 + e1 % 3] << 16);
       }
       w[6] = w[7] = 0;
-      uint4* dst = reinterpret_cast<uint4*>(o.batch + ((((int64_t)slot * (OUT / 2) + jp) * (OUT / 2) + X) << 4));
+      uint4* dst = reinterpret_cast<uint4*>(o.batch + ((((int64_t)slot * (OUT / 2) + jp0 + q) * HIPAC_S2D16_WIDTH + X + 2) << 4));
       dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
       dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
-    } else {
-#pragma unroll
-      for (int dy = 0; dy < 2; dy++)
-#pragma unroll
-        for (int dx = 0; dx < 2; dx++)
-#pragma unroll
-          for (int c = 0; c < 3; c++)
-            o.batch[(((int64_t)slot * OUT + 2 * jp + dy) * OUT + 2 * X + dx) * 3 + c] = c_lut_bf16[v[dy][dx][c] * 3 + c];
+    }
+  } else {
+    for (int rr = 0; rr < 2 * kGatherPairs; rr++) {
+      uint16_t* dst = o.batch + (((int64_t)slot * OUT + 2 * jp0 + rr) * OUT) * 3;
+      for (int k = tid; k < OUT * 3; k += 128) dst[k] = lut[rowbuf[rr][k] * 3 + k % 3];
     }
   }
 }
@@ -447,7 +461,7 @@ static int fused_scan_impl(const ScanParams& p, const OutParams& o, uint8_t* fla
     } else if (G.f == 8) {
       if (int e = launch_planes<8>(p, G, stream)) return e;
     }
-    dim3 grid((unsigned)min(n_cand, capacity), OUT / 2);
+    dim3 grid((unsigned)min(n_cand, capacity), OUT / 2 / kGatherPairs);
     ProfileScope ps("gather", stream, 0.0);
     k_gather<<<grid, 128, 0, stream>>>(p, G, o, d_coords, d_count, capacity);
     count_launch(1);

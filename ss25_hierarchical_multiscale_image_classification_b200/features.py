@@ -65,13 +65,13 @@ def pack_resnet18(state_dict: dict, device, prefix: str = "", bn_eps: float = 1e
     return PackedResNet18(torch.from_numpy(host).to(device), num_classes)
 
 
-_LAYOUT_BY_SHAPE = {(224, 224, 3): _lib.LAYOUT_NHWC3_BF16, (112, 112, 16): _lib.LAYOUT_S2D16_BF16}
+_LAYOUT_BY_SHAPE = {(224, 224, 3): _lib.LAYOUT_NHWC3_BF16, (112, 115, 16): _lib.LAYOUT_S2D16_BF16}
 
 
 def _forward(batch: torch.Tensor, packed: PackedResNet18, want_logits: bool, chunk: int, stream=None):
     l = _lib.lib()
     if not (batch.is_cuda and batch.dtype == torch.bfloat16 and batch.dim() == 4 and tuple(batch.shape[1:]) in _LAYOUT_BY_SHAPE):
-        raise ValueError("batch must be a CUDA bf16 tensor [N,224,224,3] or [N,112,112,16]")
+        raise ValueError("batch must be a CUDA bf16 tensor [N,224,224,3] or [N,112,115,16]")
     if batch.device != packed.device:
         raise ValueError("batch and packed weights live on different devices")
     if want_logits and packed.num_classes == 0:
@@ -96,12 +96,12 @@ def _forward(batch: torch.Tensor, packed: PackedResNet18, want_logits: bool, chu
     return feats, logits
 
 
-def extract_features_tensor(batch: torch.Tensor, packed: PackedResNet18, chunk: int = 128, stream=None) -> torch.Tensor:
+def extract_features_tensor(batch: torch.Tensor, packed: PackedResNet18, chunk: int = 4096, stream=None) -> torch.Tensor:
     """float32 ``[N,512]`` pooled trunk features of a bf16 patch batch (asynchronous)."""
     return _forward(batch, packed, False, chunk, stream)[0]
 
 
-def classify_tensor(batch: torch.Tensor, packed: PackedResNet18, chunk: int = 128, stream=None):
+def classify_tensor(batch: torch.Tensor, packed: PackedResNet18, chunk: int = 4096, stream=None):
     """(features float32 ``[N,512]``, logits float32 ``[N,k]``) of a bf16 patch batch (asynchronous)."""
     return _forward(batch, packed, True, chunk, stream)
 

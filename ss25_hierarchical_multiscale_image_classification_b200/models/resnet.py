@@ -41,7 +41,7 @@ class _HipacForwardMixin:
             self._pack_key = key
         return self._pack
 
-    def _run(self, x: torch.Tensor, chunk: int = 128):
+    def _run(self, x: torch.Tensor, chunk: int = 4096):
         if self.training:
             raise RuntimeError("the B200 path is inference-only: call .eval() first (training is out of scope)")
         if not x.is_cuda:
@@ -54,8 +54,8 @@ class _HipacForwardMixin:
             return _features.classify_tensor(x, packed, chunk)[1]
         return _features.extract_features_tensor(x, packed, chunk)
 
-    def forward_batch(self, batch: torch.Tensor, chunk: int = 128):
-        """Native entry: bf16 ``[N,224,224,3]`` or ``[N,112,112,16]`` batch from ``extract_patches_tensor``."""
+    def forward_batch(self, batch: torch.Tensor, chunk: int = 4096):
+        """Native entry: bf16 ``[N,224,224,3]`` or ``[N,112,115,16]`` batch from ``extract_patches_tensor``."""
         return self._run(batch, chunk)
 
 

@@ -16,6 +16,7 @@ from .. import _lib
 
 PATCH_SIZES = {0: 1792, 1: 896, 2: 448, 3: 224}   # reference src/main.py:614
 OUT = 224
+S2D16_WIDTH = 115   # 112 + explicit zero columns (2 left, 1 right), include/hipac_b200.h
 
 _LAYOUTS = {"nhwc3": _lib.LAYOUT_NHWC3_BF16, "s2d16": _lib.LAYOUT_S2D16_BF16}
 _MODES = {"auto": _lib.SCAN_AUTO, "direct": _lib.SCAN_DIRECT, "fused": _lib.SCAN_FUSED}
@@ -38,7 +39,7 @@ class PatchBatch:
     """Survivors of one ``hipac_tile_scan`` call, in the reference's emission order (x outer, y inner)."""
     coords: torch.Tensor            # int32 [N,2] (x, y) in level pixels
     labels: torch.Tensor            # uint8 [N] 1 = tumor, 0 = normal
-    batch: torch.Tensor | None      # bf16 [N,224,224,3] ("nhwc3") or [N,112,112,16] ("s2d16")
+    batch: torch.Tensor | None      # bf16 [N,224,224,3] ("nhwc3") or [N,112,115,16] ("s2d16")
     images_u8: torch.Tensor | None  # uint8 [N,224,224,3] Pillow-exact resized patches
     layout: str | None
     candidates: int
@@ -51,7 +52,7 @@ class PatchBatch:
 
 
 def batch_shape(n: int, layout: str):
-    return (n, OUT, OUT, 3) if layout == "nhwc3" else (n, OUT // 2, OUT // 2, 16)
+    return (n, OUT, OUT, 3) if layout == "nhwc3" else (n, OUT // 2, S2D16_WIDTH, 16)
 
 
 def extract_patches_tensor(level_img: torch.Tensor, lesion_mask: torch.Tensor | None, level: int,

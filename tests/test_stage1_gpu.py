@@ -74,8 +74,10 @@ def test_s2d16_layout_is_a_permutation_of_nhwc3(mode):
     assert len(a) == len(b) > 0
     x = a.batch.view(torch.int16).reshape(len(a), 112, 2, 112, 2, 3).permute(0, 1, 3, 2, 4, 5).reshape(len(a), 112, 112, 12)
     y = b.batch.view(torch.int16)
-    assert torch.equal(y[..., :12], x)
+    assert tuple(y.shape[1:]) == (112, 115, 16)                             # explicit W padding: 2 left, 1 right
+    assert torch.equal(y[:, :, 2:114, :12], x)
     assert int(y[..., 12:].abs().max()) == 0
+    assert int(y[:, :, :2].abs().max()) == 0 and int(y[:, :, 114:].abs().max()) == 0
     assert int(a.labels.sum()) == 0                                        # no mask -> all "normal"
 
 

@@ -58,8 +58,8 @@ def test_conv_layer_vs_torch_fp32(net_and_packed, layer, n):
     if relu:
         ref = torch.relu(ref)
     if layer == 0:
-        xin = torch.zeros((n, 112, 112, 16), dtype=torch.bfloat16, device="cuda")
-        xin[..., :12] = x.reshape(n, 112, 2, 112, 2, 3).permute(0, 1, 3, 2, 4, 5).reshape(n, 112, 112, 12)
+        xin = torch.zeros((n, 112, 115, 16), dtype=torch.bfloat16, device="cuda")
+        xin[:, :, 2:114, :12] = x.reshape(n, 112, 2, 112, 2, 3).permute(0, 1, 3, 2, 4, 5).reshape(n, 112, 112, 12)
     else:
         xin = x
     out = features.conv_layer(packed, layer, xin, res, relu)
@@ -83,8 +83,8 @@ def _gpu_features(packed, images_u8, layout):
     x = torch.stack([lut[:, c][u8[..., c]] for c in range(3)], dim=-1).bfloat16()     # NHWC3 bf16
     if layout == "s2d16":
         n = x.shape[0]
-        y = torch.zeros((n, 112, 112, 16), dtype=torch.bfloat16, device="cuda")
-        y[..., :12] = x.reshape(n, 112, 2, 112, 2, 3).permute(0, 1, 3, 2, 4, 5).reshape(n, 112, 112, 12)
+        y = torch.zeros((n, 112, 115, 16), dtype=torch.bfloat16, device="cuda")
+        y[:, :, 2:114, :12] = x.reshape(n, 112, 2, 112, 2, 3).permute(0, 1, 3, 2, 4, 5).reshape(n, 112, 112, 12)
         x = y
     f, lg = features.classify_tensor(x, packed, chunk=5)
     torch.cuda.synchronize()
@@ -123,7 +123,7 @@ def test_headless_packed_weights_and_errors():
     sd = {k: v for k, v in net.state_dict().items() if not k.startswith("fc.")}
     packed = features.pack_resnet18(sd, "cuda")
     assert packed.num_classes == 0
-    x = torch.zeros((2, 112, 112, 16), dtype=torch.bfloat16, device="cuda")
+    x = torch.zeros((2, 112, 115, 16), dtype=torch.bfloat16, device="cuda")
     f = features.extract_features_tensor(x, packed)
     assert f.shape == (2, 512) and torch.isfinite(f).all()
     with pytest.raises(ValueError):
