@@ -8,6 +8,7 @@
 #include <cuda.h>
 
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -40,11 +41,46 @@ constexpr int kS2dW = HIPAC_S2D16_WIDTH;  // 112 + 3 explicit zero columns (2 le
 constexpr int kABytes = kBM * 128;  // 128 rows x 64 bf16
 constexpr int kConvThreads = 192;   // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
 
+// 32 consecutive output channels of one output pixel: + folded-BN bias (+ residual) (+ ReLU) -> bf16, 64-byte store.
+__device__ __forceinline__ void epilogue_store32(const uint32_t (&v)[32], const float* __restrict__ bias,
+                                                 const __nv_bfloat16* __restrict__ residual, __nv_bfloat16* __restrict__ out,
+                                                 int relu) {
+  const float4* b4 = reinterpret_cast<const float4*>(bias);
+  uint4 res[4];
+  if (residual) {
+    const uint4* r4 = reinterpret_cast<const uint4*>(residual);
+#pragma unroll
+    for (int i = 0; i < 4; i++) res[i] = __ldg(r4 + i);
+  }
+  uint4 o[4];
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    const float4 b = __ldg(b4 + i);
+    float x0 = __uint_as_float(v[4 * i + 0]) + b.x, x1 = __uint_as_float(v[4 * i + 1]) + b.y;
+    float x2 = __uint_as_float(v[4 * i + 2]) + b.z, x3 = __uint_as_float(v[4 * i + 3]) + b.w;
+    if (residual) {
+      const uint32_t* rw = reinterpret_cast<const uint32_t*>(&res[i >> 1]) + (i & 1) * 2;
+      const __nv_bfloat162 ra = *reinterpret_cast<const __nv_bfloat162*>(&rw[0]);
+      const __nv_bfloat162 rb = *reinterpret_cast<const __nv_bfloat162*>(&rw[1]);
+      x0 += __bfloat162float(ra.x), x1 += __bfloat162float(ra.y);
+      x2 += __bfloat162float(rb.x), x3 += __bfloat162float(rb.y);
+    }
+    if (relu) x0 = fmaxf(x0, 0.f), x1 = fmaxf(x1, 0.f), x2 = fmaxf(x2, 0.f), x3 = fmaxf(x3, 0.f);
+    __nv_bfloat162 lo = __floats2bfloat162_rn(x0, x1), hi = __floats2bfloat162_rn(x2, x3);
+    uint32_t* ow = reinterpret_cast<uint32_t*>(&o[i >> 1]) + (i & 1) * 2;
+    ow[0] = *reinterpret_cast<uint32_t*>(&lo);
+    ow[1] = *reinterpret_cast<uint32_t*>(&hi);
+  }
+  uint4* dst = reinterpret_cast<uint4*>(out);
+#pragma unroll
+  for (int i = 0; i < 4; i++) dst[i] = o[i];
+}
+
 template <int BN>
 struct ConvCfg {
   static constexpr int kBBytes = BN * 128;
   static constexpr int kStage = kABytes + kBBytes;
-  static constexpr int kStages = 6;
+  static constexpr int kStages = BN == 256 ? 4 : 6;
   static constexpr int kTmemCols = 2 * BN;
   static constexpr int kSmemBytes = kStages * kStage + 1024 /*alignment slack*/ + 256 /*barriers*/;
 };
@@ -151,35 +187,7 @@ k_conv_umma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         if (valid) {
           const int n0 = n_tile * BN + c0;
           const size_t off = (size_t)m * p.cout + n0;
-          const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0);
-          uint4 res[4];
-          if (p.residual) {
-            const uint4* r4 = reinterpret_cast<const uint4*>(p.residual + off);
-#pragma unroll
-            for (int i = 0; i < 4; i++) res[i] = __ldg(r4 + i);
-          }
-          uint4 o[4];
-#pragma unroll
-          for (int i = 0; i < 8; i++) {
-            const float4 b = __ldg(b4 + i);
-            float x0 = __uint_as_float(v[4 * i + 0]) + b.x, x1 = __uint_as_float(v[4 * i + 1]) + b.y;
-            float x2 = __uint_as_float(v[4 * i + 2]) + b.z, x3 = __uint_as_float(v[4 * i + 3]) + b.w;
-            if (p.residual) {
-              const uint32_t* rw = reinterpret_cast<const uint32_t*>(&res[i >> 1]) + (i & 1) * 2;
-              const __nv_bfloat162 ra = *reinterpret_cast<const __nv_bfloat162*>(&rw[0]);
-              const __nv_bfloat162 rb = *reinterpret_cast<const __nv_bfloat162*>(&rw[1]);
-              x0 += __bfloat162float(ra.x), x1 += __bfloat162float(ra.y);
-              x2 += __bfloat162float(rb.x), x3 += __bfloat162float(rb.y);
-            }
-            if (p.relu) x0 = fmaxf(x0, 0.f), x1 = fmaxf(x1, 0.f), x2 = fmaxf(x2, 0.f), x3 = fmaxf(x3, 0.f);
-            __nv_bfloat162 lo = __floats2bfloat162_rn(x0, x1), hi = __floats2bfloat162_rn(x2, x3);
-            uint32_t* ow = reinterpret_cast<uint32_t*>(&o[i >> 1]) + (i & 1) * 2;
-            ow[0] = *reinterpret_cast<uint32_t*>(&lo);
-            ow[1] = *reinterpret_cast<uint32_t*>(&hi);
-          }
-          uint4* dst = reinterpret_cast<uint4*>(p.out + off);
-#pragma unroll
-          for (int i = 0; i < 4; i++) dst[i] = o[i];
+          epilogue_store32(v, p.bias + n0, p.residual ? p.residual + off : nullptr, p.out + off, p.relu);
         }
       }
       ptx::tc_fence_before();
@@ -194,6 +202,8 @@ k_conv_umma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   __syncthreads();
   if (warp == 1) ptx::tmem_dealloc(tmem_base, Cfg::kTmemCols);
 }
+
+#include "conv_rows.cuh"
 
 // ==========================================================================================
 // small memory-bound kernels
@@ -296,6 +306,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 static EncodeIm2colFn g_encode_im2col = nullptr;
 static EncodeTiledFn g_encode_tiled = nullptr;
 static int g_num_sms = 0;
+static bool g_use_row_kernels = true;  // HIPAC_CONV_ROWS=0 forces the im2col kernel everywhere (A/B comparison)
 
 static int init_driver_api() {
   if (g_encode_im2col && g_encode_tiled && g_num_sms) return 0;
@@ -310,6 +321,7 @@ static int init_driver_api() {
   int dev = 0;
   HIPAC_CHECK_CUDA(cudaGetDevice(&dev));
   HIPAC_CHECK_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+  if (const char* e = getenv("HIPAC_CONV_ROWS")) g_use_row_kernels = atoi(e) != 0;
   return 0;
 }
 
@@ -358,6 +370,50 @@ static int make_weight_map(CUtensorMap* map, const void* ptr, int cout, int K, i
   return 0;
 }
 
+// NHWC activation tensor as a tiled 4-D map whose box is one row-tile region: 64 channels x (w+2) x (r+2) x 1.
+static int make_region_map(CUtensorMap* map, const void* ptr, int n, int h, int w, int c, int r) {
+  cuuint64_t dims[4] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
+  cuuint64_t strides[3] = {(cuuint64_t)c * 2, (cuuint64_t)w * c * 2, (cuuint64_t)h * w * c * 2};
+  cuuint32_t box[4] = {64, (cuuint32_t)(w + 2), (cuuint32_t)(r + 2), 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult res = g_encode_tiled(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (res != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (region map) failed with CUresult " + std::to_string((int)res));
+    return -5;
+  }
+  return 0;
+}
+
+template <int BN, int KC, int W, int R, bool RESIDENT>
+static int launch_rows_t(const uint8_t* d_packed, const PackedLayout& L, int layer, const void* in, const void* residual, void* out,
+                         int n, bool relu, cudaStream_t stream, const char* name) {
+  using Cfg = RowCfg<BN, KC, W, R, RESIDENT>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    HIPAC_CHECK_CUDA(cudaFuncSetAttribute(k_conv3x3_rows<BN, KC, W, R, RESIDENT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  CUtensorMap tmA, tmB;
+  if (int e = make_region_map(&tmA, in, n, W, W, KC * 64, R)) return e;
+  if (int e = make_weight_map(&tmB, d_packed + L.w_off[layer], BN, 9 * KC * 64, BN)) return e;
+  RowConvParams p;
+  p.n_img = n, p.num_tiles = n * (W / R), p.relu = relu ? 1 : 0;
+  p.bias = reinterpret_cast<const float*>(d_packed + L.b_off[layer]);
+  p.residual = reinterpret_cast<const __nv_bfloat16*>(residual);
+  p.out = reinterpret_cast<__nv_bfloat16*>(out);
+  const int grid = p.num_tiles < g_num_sms ? p.num_tiles : g_num_sms;
+  {
+    ProfileScope ps(name, stream, 2.0 * n * W * W * BN * 9 * KC * 64);
+    k_conv3x3_rows<BN, KC, W, R, RESIDENT><<<grid, kConvThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, p);
+  }
+  count_launch(1);
+  HIPAC_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
 template <int BN>
 static int launch_conv_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvParams& p, cudaStream_t stream,
                          const char* name, double flops) {
@@ -383,6 +439,12 @@ static int run_conv(const uint8_t* d_packed, const PackedLayout& L, int layer, c
                     int n, bool relu, cudaStream_t stream) {
   const ConvSpec& cs = kConvs[layer];
   const int K = conv_gemm_k(layer);
+  if (g_use_row_kernels && cs.k == 3 && cs.stride == 1) {
+    if (cs.cin == 64 && cs.hin == 56)
+      return launch_rows_t<64, 1, 56, 2, true>(d_packed, L, layer, in, residual, out, n, relu, stream, "conv3x3_c64");
+    if (cs.cin == 128 && cs.hin == 28)
+      return launch_rows_t<128, 2, 28, 4, false>(d_packed, L, layer, in, residual, out, n, relu, stream, "conv3x3_c128");
+  }
   ConvParams p;
   p.M_total = n * cs.hout * cs.hout;
   p.hw_out = cs.hout * cs.hout, p.wout = cs.hout;
@@ -392,7 +454,7 @@ static int run_conv(const uint8_t* d_packed, const PackedLayout& L, int layer, c
   p.residual = reinterpret_cast<const __nv_bfloat16*>(residual);
   p.out = reinterpret_cast<__nv_bfloat16*>(out);
   p.num_m_tiles = (p.M_total + kBM - 1) / kBM;
-  const int bn = cs.cout >= 128 ? 128 : 64;
+  const int bn = cs.cout >= 256 ? 256 : (cs.cout >= 128 ? 128 : 64);
   p.num_n_tiles = cs.cout / bn;
   CUtensorMap tmA, tmB;
   if (int e = make_weight_map(&tmB, d_packed + L.w_off[layer], cs.cout, K, bn)) return e;
@@ -415,6 +477,7 @@ static int run_conv(const uint8_t* d_packed, const PackedLayout& L, int layer, c
   const int gi = cs.cout == 64 ? 0 : cs.cout == 128 ? 1 : cs.cout == 256 ? 2 : 3;
   const char* name = kNames[gi][cs.k == 1 ? 1 : 0];
   const double flops = 2.0 * p.M_total * cs.cout * K;
+  if (bn == 256) return launch_conv_t<256>(tmA, tmB, p, stream, name, flops);
   return bn == 128 ? launch_conv_t<128>(tmA, tmB, p, stream, name, flops) : launch_conv_t<64>(tmA, tmB, p, stream, name, flops);
 }
 
