@@ -119,8 +119,7 @@ def run_ours(args):
     import torch.distributed as dist
     import __graft_entry__ as ge
     from oracle import hipac_oracle as orc   # weights recipe only (seeded torchvision resnet18)
-    from ss25_hierarchical_multiscale_image_classification_b200 import _lib, features
-    from ss25_hierarchical_multiscale_image_classification_b200.preprocessing import extract_patches_tensor
+    from ss25_hierarchical_multiscale_image_classification_b200 import _lib, features, pipeline, sharding
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -138,48 +137,28 @@ def run_ours(args):
     img_d, msk_d = img_h.to(dev), msk_h.to(dev)
     rows = (0, i1 - i0)
     n_cand = ((WIDTH + STRIDE - 1) // STRIDE) * (i1 - i0)
-    cap = n_cand
-    # persistent host/device buffers for the e2e leg
-    img_e, msk_e = torch.empty_like(img_d), torch.empty_like(msk_d)
-    h_feats = torch.empty((cap, 512), dtype=torch.float32).pin_memory()
-    h_coords = torch.empty((cap, 2), dtype=torch.int32).pin_memory()
-    h_labels = torch.empty((cap,), dtype=torch.uint8).pin_memory()
+    pipe = pipeline.HostPipeline(int(img_h.shape[0]), WIDTH, dev, with_mask=True, num_classes=2)
 
-    def gather(pb, feats, logits):
+    def gather(r):
+        """The path's one exchange step: all-gather of counts / coords / labels / features / logits."""
         if world == 1:
-            return len(pb)
-        cnt = torch.tensor([len(pb)], dtype=torch.int64, device=dev)
-        counts = [torch.zeros_like(cnt) for _ in range(world)]
-        dist.all_gather(counts, cnt)
-        mx = int(max(int(c) for c in counts))
-        def pad(t):
-            out = torch.zeros((mx,) + tuple(t.shape[1:]), dtype=t.dtype, device=dev)
-            out[:t.shape[0]] = t
-            return out
-        coords = pb.coords.clone()
+            return len(r)
+        coords = r.coords.to(dev).clone()
         coords[:, 1] += y0
-        for t in (coords, pb.labels, feats, logits):
-            buf = torch.empty((world * mx,) + tuple(t.shape[1:]), dtype=t.dtype, device=dev)
-            dist.all_gather_into_tensor(buf, pad(t))
-        return int(sum(int(c) for c in counts))
+        out = sharding.gather_survivors({"coords": coords, "labels": r.labels.to(dev), "features": r.features.to(dev),
+                                         "logits": r.logits.to(dev)}, sort=True)
+        return int(out["coords"].shape[0])
 
     def step_resident():
-        pb = extract_patches_tensor(img_d, msk_d, LEVEL, stride=None, row_range=rows, layout="s2d16", capacity=cap)
-        feats, logits = features.classify_tensor(pb.batch, packed, chunk=args.chunk)
-        return gather(pb, feats, logits), pb
+        r = pipeline.process_level(img_d, msk_d, LEVEL, packed, stride=None, row_range=rows, chunk=args.chunk)
+        return gather(r), r
 
     def step_e2e():
-        img_e.copy_(img_h, non_blocking=True)
-        msk_e.copy_(msk_h, non_blocking=True)
-        pb = extract_patches_tensor(img_e, msk_e, LEVEL, stride=None, row_range=rows, layout="s2d16", capacity=cap)
-        feats, logits = features.classify_tensor(pb.batch, packed, chunk=args.chunk)
-        total = gather(pb, feats, logits)
-        n = len(pb)
-        h_feats[:n].copy_(feats, non_blocking=True)
-        h_coords[:n].copy_(pb.coords, non_blocking=True)
-        h_labels[:n].copy_(pb.labels, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        return total, pb
+        # host buffers in, host buffers out: pinned H2D of image + mask (overlapped with compute by row groups),
+        # D2H of coords / labels / features / logits; process_level_host synchronises before returning
+        r = pipeline.process_level_host(img_h, msk_h, LEVEL, packed, pipe, stride=None, row_range=rows,
+                                        groups=args.groups, chunk=args.chunk)
+        return gather(r), r
 
     def timed(fn, steps, warmup):
         for _ in range(warmup):
@@ -249,7 +228,7 @@ def run_ours(args):
                    "candidates_per_s": round(n_cand * world / (ms_step * 1e-3), 1),
                    "sharding": f"tile-row ranges over {world} rank(s); NCCL all-gather of counts/coords/labels/features",
                    "cache": "inputs (0.8 GB image + 0.27 GB mask per GPU) exceed the 126 MB L2; no flush needed",
-                   "resnet_chunk": args.chunk},
+                   "resnet_chunk": args.chunk, "e2e_upload_groups": args.groups},
         "e2e": {"value": round(total_surv_e / (ms_e2e * 1e-3), 1), "unit": "patches/s",
                 "h2d_bytes_per_step": int(img_h.numel() + msk_h.numel()),
                 "d2h_bytes_per_step": int(n_surv * (512 * 4 + 8 + 1) + 8), "ms_per_step": round(ms_e2e, 3)},
@@ -365,6 +344,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--chunk", type=int, default=4096, help="patches per ResNet18 chunk")
     ap.add_argument("--cpu-candidates", type=int, default=96, help="candidates in the bounded CPU-baseline sample")
+    ap.add_argument("--groups", type=int, default=4, help="row groups of the pipelined host->device upload (e2e leg)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     if args.impl == "reference":

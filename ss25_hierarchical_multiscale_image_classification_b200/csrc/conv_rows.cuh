@@ -74,26 +74,33 @@ k_conv3x3_rows(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
-      if (RESIDENT) {
+    // ===================== TMA producer (warp-uniform loop, one elected lane issues) =====================
+    {
+      if (RESIDENT && ptx::elect_one()) {
         ptx::mbar_arrive_expect_tx(&b_full[0], 9 * KC * Cfg::kBBlock);
         for (int kb = 0; kb < 9 * KC; kb++) ptx::tma_load_2d(sB + kb * Cfg::kBBlock, &tmB, &b_full[0], kb * 64, 0);
       }
+      __syncwarp();
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         const int img = tile / TILES_PER_IMG, p0 = (tile - img * TILES_PER_IMG) * R;
         for (int kc = 0; kc < KC; kc++) {
           ptx::mbar_wait(&a_empty[sa], pa ^ 1);
-          ptx::mbar_arrive_expect_tx(&a_full[sa], Cfg::kLoadBytes);
-          ptx::tma_load_4d(sA + sa * Cfg::kRegionBytes, &tmA, &a_full[sa], kc * 64, -1, p0 - 1, img);
+          if (ptx::elect_one()) {
+            ptx::mbar_arrive_expect_tx(&a_full[sa], Cfg::kLoadBytes);
+            ptx::tma_load_4d(sA + sa * Cfg::kRegionBytes, &tmA, &a_full[sa], kc * 64, -1, p0 - 1, img);
+          }
+          __syncwarp();
           if (++sa == Cfg::kAStages) sa = 0, pa ^= 1;
           if (!RESIDENT) {
             for (int tap = 0; tap < 9; tap++) {
               ptx::mbar_wait(&b_empty[sb], pb ^ 1);
-              ptx::mbar_arrive_expect_tx(&b_full[sb], Cfg::kBBlock);
-              ptx::tma_load_2d(sB + sb * Cfg::kBBlock, &tmB, &b_full[sb], (tap * KC + kc) * 64, 0);
+              if (ptx::elect_one()) {
+                ptx::mbar_arrive_expect_tx(&b_full[sb], Cfg::kBBlock);
+                ptx::tma_load_2d(sB + sb * Cfg::kBBlock, &tmB, &b_full[sb], (tap * KC + kc) * 64, 0);
+              }
+              __syncwarp();
               if (++sb == Cfg::kBStages) sb = 0, pb ^= 1;
             }
           }
@@ -101,8 +108,8 @@ k_conv3x3_rows(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (warp-uniform loop, one elected lane issues) =====================
+    {
       constexpr uint32_t idesc = ptx::make_idesc_bf16(128, BN);
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0, acc = 0, acc_phase = 0;
@@ -114,32 +121,42 @@ k_conv3x3_rows(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int kc = 0; kc < KC; kc++) {
           ptx::mbar_wait(&a_full[sa], pa);
           ptx::tc_fence_after();
-          const uint32_t a_addr = ptx::smem_u32(sA + sa * Cfg::kRegionBytes);
+          const uint64_t a_region = ptx::make_smem_desc(ptx::smem_u32(sA + sa * Cfg::kRegionBytes), 128);
+          if (RESIDENT) {
+            const uint64_t b_all = ptx::make_smem_desc(ptx::smem_u32(sB + kc * Cfg::kBBlock), 128);
+            if (ptx::elect_one()) {
+#pragma unroll
+              for (int tap = 0; tap < 9; tap++) {
+                // tap (r, s) = the staged region shifted by r*Wp + s pixels (128-byte rows): +8 per row in the address field
+                const uint64_t adesc = a_region + (uint64_t)(((tap / 3) * Wp + tap % 3) * 8);
+                const uint64_t bdesc = b_all + (uint64_t)(tap * KC * (Cfg::kBBlock >> 4));
+#pragma unroll
+                for (int k = 0; k < 4; k++) ptx::umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kc | tap | k) != 0 ? 1u : 0u);
+              }
+            }
+            __syncwarp();
+          } else {
 #pragma unroll 1
-          for (int tap = 0; tap < 9; tap++) {
-            uint32_t b_addr;
-            if (RESIDENT) {
-              b_addr = ptx::smem_u32(sB + (tap * KC + kc) * Cfg::kBBlock);
-            } else {
+            for (int tap = 0; tap < 9; tap++) {
               ptx::mbar_wait(&b_full[sb], pb);
               ptx::tc_fence_after();
-              b_addr = ptx::smem_u32(sB + sb * Cfg::kBBlock);
-            }
-            const int r = tap / 3, s = tap - 3 * r;
-            const uint32_t a_tap = a_addr + (r * Wp + s) * 128;  // shifted view of the staged region
+              const uint64_t bdesc = ptx::make_smem_desc(ptx::smem_u32(sB + sb * Cfg::kBBlock), 128);
+              const uint64_t adesc = a_region + (uint64_t)(((tap / 3) * Wp + tap % 3) * 8);
+              if (ptx::elect_one()) {
 #pragma unroll
-            for (int k = 0; k < 4; k++)
-              ptx::umma_bf16(d_tmem, ptx::make_smem_desc(a_tap + k * 32, 128), ptx::make_smem_desc(b_addr + k * 32, 128), idesc,
-                             (kc | tap | k) != 0 ? 1u : 0u);
-            if (!RESIDENT) {
-              ptx::umma_commit(&b_empty[sb]);
+                for (int k = 0; k < 4; k++) ptx::umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kc | tap | k) != 0 ? 1u : 0u);
+                ptx::umma_commit(&b_empty[sb]);
+              }
+              __syncwarp();
               if (++sb == Cfg::kBStages) sb = 0, pb ^= 1;
             }
           }
-          ptx::umma_commit(&a_empty[sa]);
+          if (ptx::elect_one()) ptx::umma_commit(&a_empty[sa]);
+          __syncwarp();
           if (++sa == Cfg::kAStages) sa = 0, pa ^= 1;
         }
-        ptx::umma_commit(&tfull[acc]);
+        if (ptx::elect_one()) ptx::umma_commit(&tfull[acc]);
+        __syncwarp();
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
@@ -154,15 +171,8 @@ k_conv3x3_rows(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       const int img = tile / TILES_PER_IMG, p0 = (tile - img * TILES_PER_IMG) * R;
       const size_t pix = ((size_t)img * H + p0 + rr) * W + x;
-      ptx::mbar_wait(&tfull[acc], acc_phase);
-      ptx::tc_fence_after();
-#pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        uint32_t v[32];
-        ptx::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(wq * 32) << 16) + acc * BN + c0, v);
-        ptx::tmem_ld_wait();
-        if (valid) epilogue_store32(v, p.bias + c0, p.residual ? p.residual + pix * BN + c0 : nullptr, p.out + pix * BN + c0, p.relu);
-      }
+      epilogue_row<BN>(tmem_base + ((uint32_t)(wq * 32) << 16) + acc * BN, p.bias, p.residual ? p.residual + pix * BN : nullptr,
+                       p.out + pix * BN, p.relu, valid, &tfull[acc], acc_phase);
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&tempty[acc]);

@@ -41,24 +41,18 @@ constexpr int kS2dW = HIPAC_S2D16_WIDTH;  // 112 + 3 explicit zero columns (2 le
 constexpr int kABytes = kBM * 128;  // 128 rows x 64 bf16
 constexpr int kConvThreads = 192;   // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
 
-// 32 consecutive output channels of one output pixel: + folded-BN bias (+ residual) (+ ReLU) -> bf16, 64-byte store.
-__device__ __forceinline__ void epilogue_store32(const uint32_t (&v)[32], const float* __restrict__ bias,
-                                                 const __nv_bfloat16* __restrict__ residual, __nv_bfloat16* __restrict__ out,
-                                                 int relu) {
+// 32 consecutive output channels of one output pixel: + folded-BN bias (+ residual, already in registers)
+// (+ ReLU) -> bf16, 64-byte store.
+__device__ __forceinline__ void epilogue_math32(const uint32_t (&v)[32], const float* __restrict__ bias, const uint4* res,
+                                                __nv_bfloat16* __restrict__ out, int relu) {
   const float4* b4 = reinterpret_cast<const float4*>(bias);
-  uint4 res[4];
-  if (residual) {
-    const uint4* r4 = reinterpret_cast<const uint4*>(residual);
-#pragma unroll
-    for (int i = 0; i < 4; i++) res[i] = __ldg(r4 + i);
-  }
   uint4 o[4];
 #pragma unroll
   for (int i = 0; i < 8; i++) {
     const float4 b = __ldg(b4 + i);
     float x0 = __uint_as_float(v[4 * i + 0]) + b.x, x1 = __uint_as_float(v[4 * i + 1]) + b.y;
     float x2 = __uint_as_float(v[4 * i + 2]) + b.z, x3 = __uint_as_float(v[4 * i + 3]) + b.w;
-    if (residual) {
+    if (res) {
       const uint32_t* rw = reinterpret_cast<const uint32_t*>(&res[i >> 1]) + (i & 1) * 2;
       const __nv_bfloat162 ra = *reinterpret_cast<const __nv_bfloat162*>(&rw[0]);
       const __nv_bfloat162 rb = *reinterpret_cast<const __nv_bfloat162*>(&rw[1]);
@@ -74,6 +68,40 @@ __device__ __forceinline__ void epilogue_store32(const uint32_t (&v)[32], const 
   uint4* dst = reinterpret_cast<uint4*>(out);
 #pragma unroll
   for (int i = 0; i < 4; i++) dst[i] = o[i];
+}
+
+// Epilogue of one accumulator row (BN channels of one output pixel).  The residual row is fetched into
+// registers BEFORE waiting for the accumulator (its address does not depend on the MMAs), so its global-load
+// latency hides behind the tile's main loop; TMEM is drained 64 columns per wait.
+template <int BN>
+__device__ __forceinline__ void epilogue_row(uint32_t tmem_row, const float* __restrict__ bias,
+                                             const __nv_bfloat16* __restrict__ residual_row, __nv_bfloat16* __restrict__ out_row,
+                                             int relu, bool valid, uint64_t* tfull_bar, uint32_t phase) {
+  constexpr bool kPrefetch = BN <= 128;  // 16 B per 8 channels: 32 (BN=64) / 64 (BN=128) registers
+  uint4 res[kPrefetch ? BN / 8 : 8];
+  const bool has_res = residual_row != nullptr && valid;
+  if (kPrefetch && has_res) {
+#pragma unroll
+    for (int i = 0; i < BN / 8; i++) res[i] = __ldg(reinterpret_cast<const uint4*>(residual_row) + i);
+  }
+  ptx::mbar_wait(tfull_bar, phase);
+  ptx::tc_fence_after();
+#pragma unroll
+  for (int c0 = 0; c0 < BN; c0 += 64) {
+    uint32_t v0[32], v1[32];
+    ptx::tmem_ld_32x32b_x32(tmem_row + c0, v0);
+    ptx::tmem_ld_32x32b_x32(tmem_row + c0 + 32, v1);
+    if (!kPrefetch && has_res) {
+#pragma unroll
+      for (int i = 0; i < 8; i++) res[i] = __ldg(reinterpret_cast<const uint4*>(residual_row + c0) + i);
+    }
+    ptx::tmem_ld_wait();
+    if (valid) {
+      const uint4* r0 = has_res ? &res[kPrefetch ? c0 / 8 : 0] : nullptr;
+      epilogue_math32(v0, bias + c0, r0, out_row + c0, relu);
+      epilogue_math32(v1, bias + c0 + 32, has_res ? r0 + 4 : nullptr, out_row + c0 + 32, relu);
+    }
+  }
 }
 
 template <int BN>
@@ -117,7 +145,9 @@ k_conv_umma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    // The whole warp runs the loop with warp-uniform values (descriptors and coordinates then live in uniform
+    // registers); one elected lane issues the TMA instructions.
+    {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -128,20 +158,24 @@ k_conv_umma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const int cw = q0 * p.stride - p.pad_w, ch = p0 * p.stride - p.pad_h;
         for (int kb = 0; kb < p.num_kb; kb++) {
           ptx::mbar_wait(&empty[stage], phase ^ 1);
-          ptx::mbar_arrive_expect_tx(&full[stage], Cfg::kStage);
           uint8_t* a_dst = base + stage * Cfg::kStage;
           uint8_t* b_dst = a_dst + kABytes;
           const int tap = kb / p.kc_blocks, kc = kb - tap * p.kc_blocks;
           const int r = tap / p.kw, s = tap - r * p.kw;
-          ptx::tma_load_im2col_4d(a_dst, &tmA, &full[stage], kc * 64, cw, ch, img, (uint16_t)s, (uint16_t)r);
-          ptx::tma_load_2d(b_dst, &tmB, &full[stage], kb * 64, n_tile * BN);
+          if (ptx::elect_one()) {
+            ptx::mbar_arrive_expect_tx(&full[stage], Cfg::kStage);
+            ptx::tma_load_im2col_4d(a_dst, &tmA, &full[stage], kc * 64, cw, ch, img, (uint16_t)s, (uint16_t)r);
+            ptx::tma_load_2d(b_dst, &tmB, &full[stage], kb * 64, n_tile * BN);
+          }
+          __syncwarp();
           if (++stage == Cfg::kStages) stage = 0, phase ^= 1;
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (one thread) =====================
-    if (lane == 0) {
+    // ===================== MMA issuer =====================
+    // Warp-uniform loop; one elected lane (always the same one) issues the UMMAs and their commits.
+    {
       constexpr uint32_t idesc = ptx::make_idesc_bf16(kBM, BN);
       int stage = 0;
       uint32_t phase = 0, acc = 0, acc_phase = 0;
@@ -153,17 +187,18 @@ k_conv_umma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           ptx::mbar_wait(&full[stage], phase);
           ptx::tc_fence_after();
           const uint32_t a_addr = ptx::smem_u32(base + stage * Cfg::kStage);
-          const uint32_t b_addr = a_addr + kABytes;
+          const uint64_t adesc = ptx::make_smem_desc(a_addr, 128), bdesc = ptx::make_smem_desc(a_addr + kABytes, 128);
+          if (ptx::elect_one()) {
 #pragma unroll
-          for (int k = 0; k < 4; k++) {  // 4 x (K = 16) per 64-wide k-block
-            const uint64_t adesc = ptx::make_smem_desc(a_addr + k * 32, 128);
-            const uint64_t bdesc = ptx::make_smem_desc(b_addr + k * 32, 128);
-            ptx::umma_bf16(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < 4; k++)  // 4 x (K = 16) per 64-wide k-block: +32 B = +2 in the descriptor's address field
+              ptx::umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            ptx::umma_commit(&empty[stage]);  // smem slot reusable once these MMAs retire
           }
-          ptx::umma_commit(&empty[stage]);  // smem slot reusable once these MMAs retire
+          __syncwarp();
           if (++stage == Cfg::kStages) stage = 0, phase ^= 1;
         }
-        ptx::umma_commit(&tfull[acc]);  // accumulator complete -> epilogue
+        if (ptx::elect_one()) ptx::umma_commit(&tfull[acc]);  // accumulator complete -> epilogue
+        __syncwarp();
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
@@ -177,18 +212,10 @@ k_conv_umma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const int m_tile = tile / p.num_n_tiles, n_tile = tile - m_tile * p.num_n_tiles;
       const int m = m_tile * kBM + row;
       const bool valid = m < p.M_total;
-      ptx::mbar_wait(&tfull[acc], acc_phase);
-      ptx::tc_fence_after();
-#pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        uint32_t v[32];
-        ptx::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(wq * 32) << 16) + acc * BN + c0, v);
-        ptx::tmem_ld_wait();
-        if (valid) {
-          const int n0 = n_tile * BN + c0;
-          const size_t off = (size_t)m * p.cout + n0;
-          epilogue_store32(v, p.bias + n0, p.residual ? p.residual + off : nullptr, p.out + off, p.relu);
-        }
+      {
+        const size_t off = (size_t)m * p.cout + (size_t)n_tile * BN;
+        epilogue_row<BN>(tmem_base + ((uint32_t)(wq * 32) << 16) + acc * BN, p.bias + n_tile * BN,
+                         p.residual ? p.residual + off : nullptr, p.out + off, p.relu, valid, &tfull[acc], acc_phase);
       }
       ptx::tc_fence_before();
       __syncwarp();

@@ -1,0 +1,114 @@
+"""One level image -> survivors' coordinates, labels, 512-d features and logits, without the PNG round trip.
+
+This is the device-resident composition of the reference's two stages -- ``extract_patches``
+(``src/main.py:609-732``) feeding ``extract_features`` (``src/main.py:805-894``) through PNG files -- as
+one pass: ``hipac_tile_scan`` writes the normalised bf16 batch that ``hipac_resnet18_forward`` consumes.
+
+``process_level``       inputs already in HBM.
+``process_level_host``  inputs in (pinned) host memory: the upload is cut into row groups and overlapped
+                        with the tile scan + ResNet18 of the previous group on a second stream, and the
+                        results come back into host buffers.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import torch
+
+from . import features as _features
+from .preprocessing.tensor_api import extract_patches_tensor, grid_shape, patch_and_stride
+
+
+@dataclass
+class LevelResult:
+    coords: torch.Tensor        # int32 [N,2] (x, y) level pixels, reference emission order within each row group
+    labels: torch.Tensor        # uint8 [N]
+    features: torch.Tensor      # float32 [N,512]
+    logits: torch.Tensor | None  # float32 [N,k]
+    candidates: int
+
+    def __len__(self):
+        return int(self.coords.shape[0])
+
+
+def process_level(level_img: torch.Tensor, lesion_mask, level: int, packed: _features.PackedResNet18, stride=None,
+                  row_range=None, chunk: int = 4096, mode: str = "auto") -> LevelResult:
+    """Tile + tissue/lesion mask + ResNet18 features of a level image resident on the GPU."""
+    pb = extract_patches_tensor(level_img, lesion_mask, level, stride=stride, row_range=row_range, layout="s2d16", mode=mode)
+    if packed.num_classes > 0:
+        feats, logits = _features.classify_tensor(pb.batch, packed, chunk)
+    else:
+        feats, logits = _features.extract_features_tensor(pb.batch, packed, chunk), None
+    return LevelResult(pb.coords, pb.labels, feats, logits, pb.candidates)
+
+
+class HostPipeline:
+    """Reusable device/host staging buffers + copy stream for ``process_level_host``."""
+
+    def __init__(self, height: int, width: int, device, with_mask: bool = True, capacity: int | None = None,
+                 num_classes: int = 2):
+        self.device = torch.device(device)
+        self.img = torch.empty((height, width, 3), dtype=torch.uint8, device=self.device)
+        self.mask = torch.empty((height, width), dtype=torch.uint8, device=self.device) if with_mask else None
+        self.copy_stream = torch.cuda.Stream(self.device)
+        self.capacity = capacity
+        self.num_classes = num_classes
+        self._host = None
+
+    def host_buffers(self, cap: int):
+        if self._host is None or self._host[0].shape[0] < cap:
+            self._host = (torch.empty((cap, 2), dtype=torch.int32).pin_memory(),
+                          torch.empty((cap,), dtype=torch.uint8).pin_memory(),
+                          torch.empty((cap, 512), dtype=torch.float32).pin_memory(),
+                          torch.empty((cap, max(self.num_classes, 1)), dtype=torch.float32).pin_memory())
+        return self._host
+
+
+def process_level_host(level_img_host: torch.Tensor, mask_host, level: int, packed: _features.PackedResNet18,
+                       pipe: HostPipeline, stride=None, row_range=None, groups: int = 4, chunk: int = 4096) -> LevelResult:
+    """Same as ``process_level`` for HOST inputs; returns HOST tensors (pinned views, valid until the next call).
+
+    The candidate grid rows are cut into ``groups`` contiguous groups.  All uploads are queued in row order
+    on the copy stream; group ``g`` is scanned as soon as the rows it touches (its own + the
+    ``patch - stride`` halo) have landed, while the rest of the image is still in flight."""
+    H, W = int(level_img_host.shape[0]), int(level_img_host.shape[1])
+    P, S = patch_and_stride(level, stride)
+    nx, ny_all = grid_shape(W, H, S)
+    i0, i1 = (0, ny_all) if row_range is None else row_range
+    groups = max(1, min(groups, i1 - i0))
+    bounds = [i0 + (i1 - i0) * g // groups for g in range(groups + 1)]
+    dev = pipe.device
+    main = torch.cuda.current_stream(dev)
+    events, done_rows = [], i0 * S
+    with torch.cuda.stream(pipe.copy_stream):
+        pipe.copy_stream.wait_stream(main)          # previous step's kernels are done with the staging buffers
+        for g in range(groups):
+            need = min(H, (bounds[g + 1] - 1) * S + P + 8) if bounds[g + 1] > bounds[g] else done_rows
+            if need > done_rows:
+                pipe.img[done_rows:need].copy_(level_img_host[done_rows:need], non_blocking=True)
+                if pipe.mask is not None and mask_host is not None:
+                    pipe.mask[done_rows:need].copy_(mask_host[done_rows:need], non_blocking=True)
+                done_rows = need
+            ev = torch.cuda.Event()
+            ev.record(pipe.copy_stream)
+            events.append(ev)
+    cap = nx * (i1 - i0)
+    h_coords, h_labels, h_feats, h_logits = pipe.host_buffers(cap)
+    n_total, n_cand = 0, 0
+    mask_dev = pipe.mask if (pipe.mask is not None and mask_host is not None) else None
+    for g in range(groups):
+        if bounds[g + 1] <= bounds[g]:
+            continue
+        main.wait_event(events[g])
+        r = process_level(pipe.img, mask_dev, level, packed, stride=stride, row_range=(bounds[g], bounds[g + 1]), chunk=chunk)
+        n = len(r)
+        h_coords[n_total:n_total + n].copy_(r.coords, non_blocking=True)
+        h_labels[n_total:n_total + n].copy_(r.labels, non_blocking=True)
+        h_feats[n_total:n_total + n].copy_(r.features, non_blocking=True)
+        if r.logits is not None:
+            h_logits[n_total:n_total + n].copy_(r.logits, non_blocking=True)
+        n_total += n
+        n_cand += r.candidates
+    main.synchronize()
+    return LevelResult(h_coords[:n_total], h_labels[:n_total], h_feats[:n_total],
+                       h_logits[:n_total] if packed.num_classes > 0 else None, n_cand)

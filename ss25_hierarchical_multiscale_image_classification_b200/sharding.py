@@ -1,0 +1,65 @@
+"""Tile-row sharding of the candidate grid across ranks and the one exchange step of the path.
+
+The reference has no multi-GPU support on this path (``nn.DataParallel`` wraps a model that is never
+run, ``src/main.py:839-842``).  Here the unit of work is one candidate patch; ranks own contiguous
+candidate *grid rows* (``y // stride``) and need no data-path collective: the only exchange is the
+variable-length gather of per-rank survivor counts, coordinates, labels, features and logits
+(SURVEY.md section 8e).  Works with any ``torch.distributed`` backend (NCCL on the GPUs, gloo in the CPU
+tests); nothing here touches pixels.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+
+def shard_rows(ny_total: int, world: int, rank: int):
+    """Contiguous candidate grid-row range ``[i0, i1)`` of ``rank``; sizes differ by at most one row."""
+    if not (0 <= rank < world):
+        raise ValueError(f"rank {rank} outside world of {world}")
+    base, rem = divmod(ny_total, world)
+    i0 = rank * base + min(rank, rem)
+    return i0, i0 + base + (1 if rank < rem else 0)
+
+
+def slab_rows(i0: int, i1: int, stride: int, patch: int, height: int):
+    """Level rows ``[y0, y1)`` a rank must hold to tile grid rows ``[i0, i1)``: its own rows plus a
+    read-only halo of ``patch - stride`` rows (no inter-GPU halo exchange: the source is the host)."""
+    if i1 <= i0:
+        return i0 * stride, i0 * stride
+    return i0 * stride, min(height, (i1 - 1) * stride + patch)
+
+
+def canonical_order(coords: torch.Tensor) -> torch.Tensor:
+    """Permutation that sorts ``(x, y)`` rows into the reference's emission order (x outer, y inner)."""
+    key = coords[:, 0].to(torch.int64) * (1 << 32) + coords[:, 1].to(torch.int64)
+    return torch.argsort(key, stable=True)
+
+
+def gather_survivors(tensors: dict, group=None, sort: bool = True) -> dict:
+    """All-gather variable-length per-rank results.
+
+    ``tensors`` maps names to tensors whose first dimension is this rank's survivor count (it must contain
+    ``"coords"`` int32 ``[n,2]`` in GLOBAL level coordinates).  Every rank returns the concatenation over
+    ranks, in canonical ``(x, y)`` order when ``sort`` -- array-equal to a single-rank run."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if world == 1:
+        out = dict(tensors)
+    else:
+        ref = tensors["coords"]
+        n = torch.tensor([ref.shape[0]], dtype=torch.int64, device=ref.device)
+        counts = [torch.zeros_like(n) for _ in range(world)]
+        dist.all_gather(counts, n, group=group)
+        counts = [int(c) for c in counts]
+        mx = max(counts) if counts else 0
+        out = {}
+        for name, t in tensors.items():
+            pad = torch.zeros((mx,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+            pad[: t.shape[0]] = t
+            buf = torch.empty((world * mx,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+            dist.all_gather_into_tensor(buf, pad.contiguous(), group=group)
+            out[name] = torch.cat([buf[r * mx: r * mx + counts[r]] for r in range(world)])
+    if sort and out["coords"].shape[0]:
+        perm = canonical_order(out["coords"])
+        out = {k: v[perm] for k, v in out.items()}
+    return out
