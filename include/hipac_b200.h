@@ -115,6 +115,9 @@ int hipac_resnet18_conv_layer(const void* d_packed, int num_classes, int layer,
                               const void* d_in, const void* d_residual, void* d_out,
                               int n_patches, int relu, void* stream);
 
+/* Test hook: the fused stem (conv1 + folded BN + ReLU + 3x3/s2 max pool): S2D16 batch -> bf16 [n][56][56][64]. */
+int hipac_resnet18_stem(const void* d_packed, int num_classes, const void* d_in, void* d_out, int n_patches, void* stream);
+
 /* Number of kernel launches issued by this library on the calling thread since the last reset
  * (bench.py's "gpu_launches"). */
 long long hipac_launch_count(int reset);

@@ -1,0 +1,207 @@
+// Fused stem: conv1 (7x7 / stride 2 / pad 3, 3 -> 64, folded BN, ReLU) + MaxPool 3x3 / stride 2 / pad 1,
+// bf16 space-to-depth batch [n][112][115][16] -> bf16 NHWC [n][56][56][64].  Included by resnet18.cu.
+//
+// conv1 over the 2x2 space-to-depth image is a 4x4 / stride-1 filter over 16-channel pixels (32 B).  One
+// M-tile is ONE conv output row (112 positions of the 128 UMMA rows).  A CTA works on blocks of 8 pooled
+// rows = 17 conv rows: a single TMA box brings the 20 space-to-depth rows the block touches into shared
+// memory (double buffered across blocks; H padding by TMA zero fill, W padding is stored in the batch),
+// and each of the 16 filter taps of each conv row is an UMMA whose A descriptor is that region shifted by
+// (row + a) * 115 + b pixels (32-byte rows, 32-byte swizzle).  The weights (64 x 256 bf16 = 32 KB) stay
+// resident.  The epilogue never writes the 112 x 112 x 64 conv output: it keeps the running vertical max
+// of the current pooled row in shared memory, and every second conv row takes the horizontal 3-max and
+// stores one pooled row.  Post-ReLU values are >= 0, so the pool's -inf padding is equivalent to skipping
+// the out-of-range taps.
+#pragma once
+
+constexpr int kStemPB = 8;                        // pooled rows per block (56 = 7 * 8)
+constexpr int kStemRows = 2 * kStemPB + 4;        // space-to-depth rows per block region
+constexpr int kStemRegionLoad = kStemRows * kS2dW * 32;
+constexpr int kStemRegionBytes = (kStemRegionLoad + 128 * 32 + 1023) / 1024 * 1024;  // + slack for the 128-row UMMA window
+constexpr int kStemWBytes = 64 * 256 * 2;
+constexpr int kStemVBytes = 112 * 128;            // one conv row of bf16 [112][64]
+constexpr int kStemSmem = 2 * kStemRegionBytes + kStemWBytes + kStemVBytes + 1024 + 256;
+
+struct StemParams {
+  int num_blocks;  // n_img * (56 / kStemPB)
+  const float* bias;
+  __nv_bfloat16* out;  // [n][56][56][64]
+};
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+__device__ __forceinline__ uint4 bf16x8_max(uint4 a, uint4 b) {
+  uint4 r;
+  const __nv_bfloat162* pa = reinterpret_cast<const __nv_bfloat162*>(&a);
+  const __nv_bfloat162* pb = reinterpret_cast<const __nv_bfloat162*>(&b);
+  __nv_bfloat162* pr = reinterpret_cast<__nv_bfloat162*>(&r);
+#pragma unroll
+  for (int i = 0; i < 4; i++) pr[i] = __hmax2(pa[i], pb[i]);
+  return r;
+}
+
+__global__ void __launch_bounds__(kConvThreads, 1)
+k_conv1_pool(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const StemParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = base;                                   // 2 block regions
+  uint8_t* sW = base + 2 * kStemRegionBytes;            // resident weights, 4 k-blocks of [64 x 64] (128B swizzle)
+  uint8_t* sV = sW + kStemWBytes;                       // running vertical max [112][64] bf16, 16B chunks XOR-swizzled
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(sV + kStemVBytes);
+  uint64_t* a_empty = a_full + 2;
+  uint64_t* w_full = a_empty + 2;
+  uint64_t* tfull = w_full + 1;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    ptx::prefetch_tensormap(&tmA);
+    ptx::prefetch_tensormap(&tmB);
+    for (int s = 0; s < 2; s++) ptx::mbar_init(&a_full[s], 1), ptx::mbar_init(&a_empty[s], 1);
+    ptx::mbar_init(w_full, 1);
+    for (int a = 0; a < 2; a++) ptx::mbar_init(&tfull[a], 1), ptx::mbar_init(&tempty[a], 4);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_slot, 128);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  constexpr int BLOCKS_PER_IMG = 56 / kStemPB;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (ptx::elect_one()) {
+      ptx::mbar_arrive_expect_tx(w_full, kStemWBytes);
+      for (int kb = 0; kb < 4; kb++) ptx::tma_load_2d(sW + kb * 8192, &tmB, w_full, kb * 64, 0);
+    }
+    __syncwarp();
+    int s = 0;
+    uint32_t ph = 0;
+    for (int blk = blockIdx.x; blk < p.num_blocks; blk += gridDim.x) {
+      const int img = blk / BLOCKS_PER_IMG, py0 = (blk - img * BLOCKS_PER_IMG) * kStemPB;
+      ptx::mbar_wait(&a_empty[s], ph ^ 1);
+      if (ptx::elect_one()) {
+        ptx::mbar_arrive_expect_tx(&a_full[s], kStemRegionLoad);
+        ptx::tma_load_4d(sA + s * kStemRegionBytes, &tmA, &a_full[s], 0, 0, 2 * py0 - 3, img);
+      }
+      __syncwarp();
+      if (++s == 2) s = 0, ph ^= 1;
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc = ptx::make_idesc_bf16(128, 64);
+    ptx::mbar_wait(w_full, 0);
+    const uint64_t wdesc = ptx::make_smem_desc(ptx::smem_u32(sW), 128);
+    int s = 0;
+    uint32_t ph = 0, acc = 0, acc_phase = 0;
+    for (int blk = blockIdx.x; blk < p.num_blocks; blk += gridDim.x) {
+      const int py0 = (blk % BLOCKS_PER_IMG) * kStemPB;
+      ptx::mbar_wait(&a_full[s], ph);
+      ptx::tc_fence_after();
+      const uint64_t rdesc = ptx::make_smem_desc(ptx::smem_u32(sA + s * kStemRegionBytes), 32);
+      for (int t = (py0 == 0 ? 1 : 0); t <= 2 * kStemPB; t++) {  // conv row 2*py0 - 1 + t (row -1 does not exist)
+        ptx::mbar_wait(&tempty[acc], acc_phase ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * 64;
+        if (ptx::elect_one()) {
+#pragma unroll
+          for (int a = 0; a < 4; a++)
+#pragma unroll
+            for (int b = 0; b < 4; b++)
+              ptx::umma_bf16(d_tmem, rdesc + (uint64_t)(((t + a) * kS2dW + b) * 2), wdesc + (uint64_t)(a * 512 + b * 2), idesc,
+                             (a | b) != 0 ? 1u : 0u);
+          ptx::umma_commit(&tfull[acc]);
+        }
+        __syncwarp();
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+      if (ptx::elect_one()) ptx::umma_commit(&a_empty[s]);
+      __syncwarp();
+      if (++s == 2) s = 0, ph ^= 1;
+    }
+  } else {
+    // ===================== epilogue: bias + ReLU -> running max -> pooled row =====================
+    const int wq = warp & 3;
+    const int x = wq * 32 + lane;  // conv column of this thread's accumulator row
+    const int et = threadIdx.x - 64;  // 0..127 among the epilogue threads
+    const bool valid = x < 112;
+    uint32_t acc = 0, acc_phase = 0;
+    for (int blk = blockIdx.x; blk < p.num_blocks; blk += gridDim.x) {
+      const int img = blk / BLOCKS_PER_IMG, py0 = (blk - img * BLOCKS_PER_IMG) * kStemPB;
+      for (int t = (py0 == 0 ? 1 : 0); t <= 2 * kStemPB; t++) {
+        const bool init = t == (py0 == 0 ? 1 : 0);    // first conv row of the block starts the running max
+        const bool closes = t > 0 && (t & 1) == 0;    // conv row 2*py + 1: pooled row py = py0 + t/2 - 1 is complete
+        ptx::mbar_wait(&tfull[acc], acc_phase);
+        ptx::tc_fence_after();
+        uint32_t v0[32], v1[32];
+        ptx::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(wq * 32) << 16) + acc * 64, v0);
+        ptx::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(wq * 32) << 16) + acc * 64 + 32, v1);
+        ptx::tmem_ld_wait();
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&tempty[acc]);   // accumulator drained into registers
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+        uint4 cur[8];  // this pixel's 64 channels, bf16
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+          const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias) + i);
+          const uint32_t* src = i < 8 ? &v0[4 * i] : &v1[4 * (i - 8)];
+          const float y0 = fmaxf(__uint_as_float(src[0]) + b.x, 0.f), y1 = fmaxf(__uint_as_float(src[1]) + b.y, 0.f);
+          const float y2 = fmaxf(__uint_as_float(src[2]) + b.z, 0.f), y3 = fmaxf(__uint_as_float(src[3]) + b.w, 0.f);
+          __nv_bfloat162 lo = __floats2bfloat162_rn(y0, y1), hi = __floats2bfloat162_rn(y2, y3);
+          uint32_t* dst = reinterpret_cast<uint32_t*>(&cur[i >> 1]) + (i & 1) * 2;
+          dst[0] = *reinterpret_cast<uint32_t*>(&lo);
+          dst[1] = *reinterpret_cast<uint32_t*>(&hi);
+        }
+        if (valid) {
+          uint4* mine = reinterpret_cast<uint4*>(sV + x * 128);
+#pragma unroll
+          for (int j = 0; j < 8; j++) {
+            const int jj = j ^ (x & 7);  // XOR swizzle: conflict-free 16-byte accesses at a 128-byte row stride
+            mine[jj] = init ? cur[j] : bf16x8_max(mine[jj], cur[j]);
+          }
+        }
+        if (closes) {
+          // the running max is complete: horizontal 3-max, then restart it from this (shared) odd conv row
+          named_bar_sync(1, 128);
+          if (et < 112) {
+            // thread -> (pooled column px, channel half): 3-max over conv columns 2px-1, 2px, 2px+1
+            const int px = et >> 1, half = et & 1;
+            const int py = py0 + (t >> 1) - 1;
+            uint4 m[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) m[j] = reinterpret_cast<const uint4*>(sV + (2 * px) * 128)[(half * 4 + j) ^ ((2 * px) & 7)];
+            if (px > 0) {
+#pragma unroll
+              for (int j = 0; j < 4; j++)
+                m[j] = bf16x8_max(m[j], reinterpret_cast<const uint4*>(sV + (2 * px - 1) * 128)[(half * 4 + j) ^ ((2 * px - 1) & 7)]);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+              m[j] = bf16x8_max(m[j], reinterpret_cast<const uint4*>(sV + (2 * px + 1) * 128)[(half * 4 + j) ^ ((2 * px + 1) & 7)]);
+            uint4* dst = reinterpret_cast<uint4*>(p.out + (((size_t)img * 56 + py) * 56 + px) * 64 + half * 32);
+#pragma unroll
+            for (int j = 0; j < 4; j++) dst[j] = m[j];
+          }
+          named_bar_sync(1, 128);  // everyone has read its neighbours' columns
+          if (valid) {
+            uint4* mine = reinterpret_cast<uint4*>(sV + x * 128);
+#pragma unroll
+            for (int j = 0; j < 8; j++) mine[j ^ (x & 7)] = cur[j];
+          }
+        }
+      }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc(tmem_base, 128);
+}

@@ -231,6 +231,7 @@ k_conv_umma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 }
 
 #include "conv_rows.cuh"
+#include "conv_stem.cuh"
 
 // ==========================================================================================
 // small memory-bound kernels
@@ -333,6 +334,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 static EncodeIm2colFn g_encode_im2col = nullptr;
 static EncodeTiledFn g_encode_tiled = nullptr;
 static int g_num_sms = 0;
+static bool g_use_fused_stem = true;   // HIPAC_FUSED_STEM=0 runs conv1 and the max pool as two kernels
 static bool g_use_row_kernels = true;  // HIPAC_CONV_ROWS=0 forces the im2col kernel everywhere (A/B comparison)
 
 static int init_driver_api() {
@@ -349,6 +351,7 @@ static int init_driver_api() {
   HIPAC_CHECK_CUDA(cudaGetDevice(&dev));
   HIPAC_CHECK_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
   if (const char* e = getenv("HIPAC_CONV_ROWS")) g_use_row_kernels = atoi(e) != 0;
+  if (const char* e = getenv("HIPAC_FUSED_STEM")) g_use_fused_stem = atoi(e) != 0;
   return 0;
 }
 
@@ -435,6 +438,42 @@ static int launch_rows_t(const uint8_t* d_packed, const PackedLayout& L, int lay
   {
     ProfileScope ps(name, stream, 2.0 * n * W * W * BN * 9 * KC * 64);
     k_conv3x3_rows<BN, KC, W, R, RESIDENT><<<grid, kConvThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, p);
+  }
+  count_launch(1);
+  HIPAC_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// Fused conv1 + BN + ReLU + maxpool on the S2D16 batch -> [n][56][56][64].
+static int run_stem(const uint8_t* d_packed, const PackedLayout& L, const void* in, void* out, int n, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    HIPAC_CHECK_CUDA(cudaFuncSetAttribute(k_conv1_pool, cudaFuncAttributeMaxDynamicSharedMemorySize, kStemSmem));
+    attr_set = true;
+  }
+  CUtensorMap tmA, tmB;
+  {
+    cuuint64_t dims[4] = {16, (cuuint64_t)kS2dW, 112, (cuuint64_t)n};
+    cuuint64_t strides[3] = {32, (cuuint64_t)kS2dW * 32, (cuuint64_t)112 * kS2dW * 32};
+    cuuint32_t box[4] = {16, (cuuint32_t)kS2dW, (cuuint32_t)kStemRows, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult res = g_encode_tiled(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(in), dims, strides, box, estr,
+                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (res != CUDA_SUCCESS) {
+      set_error("cuTensorMapEncodeTiled (stem region map) failed with CUresult " + std::to_string((int)res));
+      return -5;
+    }
+  }
+  if (int e = make_weight_map(&tmB, d_packed + L.w_off[0], 64, 256, 64)) return e;
+  StemParams p;
+  p.num_blocks = n * (56 / kStemPB);
+  p.bias = reinterpret_cast<const float*>(d_packed + L.b_off[0]);
+  p.out = reinterpret_cast<__nv_bfloat16*>(out);
+  const int grid = p.num_blocks < g_num_sms ? p.num_blocks : g_num_sms;
+  {
+    ProfileScope ps("conv1_pool_fused", stream, 2.0 * n * 112 * 112 * 64 * 147);
+    k_conv1_pool<<<grid, kConvThreads, kStemSmem, stream>>>(tmA, tmB, p);
   }
   count_launch(1);
   HIPAC_CHECK_CUDA(cudaGetLastError());
@@ -596,6 +635,14 @@ extern "C" int hipac_resnet18_conv_layer(const void* d_packed, int num_classes, 
                   (cudaStream_t)stream_);
 }
 
+extern "C" int hipac_resnet18_stem(const void* d_packed, int num_classes, const void* d_in, void* d_out, int n_patches,
+                                   void* stream_) {
+  HIPAC_REQUIRE(d_packed && d_in && d_out && n_patches > 0, "bad arguments");
+  if (int e = init_driver_api()) return e;
+  const PackedLayout L = packed_layout(num_classes);
+  return run_stem(reinterpret_cast<const uint8_t*>(d_packed), L, d_in, d_out, n_patches, (cudaStream_t)stream_);
+}
+
 extern "C" int hipac_resnet18_forward(const void* d_packed, int num_classes, const void* d_batch, int layout, int n_patches,
                                       float* d_feats, float* d_logits, void* d_workspace, size_t workspace_bytes, int chunk,
                                       void* stream_) {
@@ -642,12 +689,16 @@ extern "C" int hipac_resnet18_forward(const void* d_packed, int num_classes, con
       return run_conv(pk, L, layer, in, res, out, n, relu, stream);
     };
     int e = 0;
-    if ((e = conv(0, x0, nullptr, c1, true))) return e;
-    {
-      ProfileScope ps("maxpool3x3s2", stream, (double)n * (kC1Bytes + kActBytes));
-      k_maxpool<<<g_num_sms * 8, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(c1), reinterpret_cast<__nv_bfloat16*>(A), n);
+    if (g_use_fused_stem) {
+      if ((e = run_stem(pk, L, x0, A, n, stream))) return e;
+    } else {
+      if ((e = conv(0, x0, nullptr, c1, true))) return e;
+      {
+        ProfileScope ps("maxpool3x3s2", stream, (double)n * (kC1Bytes + kActBytes));
+        k_maxpool<<<g_num_sms * 8, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(c1), reinterpret_cast<__nv_bfloat16*>(A), n);
+      }
+      count_launch(1);
     }
-    count_launch(1);
     // layer1 (two basic blocks, identity shortcuts)
     if ((e = conv(1, A, nullptr, B, true)) || (e = conv(2, B, A, C, true))) return e;
     if ((e = conv(3, C, nullptr, B, true)) || (e = conv(4, B, C, A, true))) return e;

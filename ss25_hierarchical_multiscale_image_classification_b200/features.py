@@ -120,3 +120,14 @@ def conv_layer(packed: PackedResNet18, layer: int, x: torch.Tensor, residual: to
                                      out.data_ptr(), n, int(relu), st.cuda_stream)
     _lib.check(rc, "hipac_resnet18_conv_layer")
     return out
+
+
+def stem(packed: PackedResNet18, x: torch.Tensor) -> torch.Tensor:
+    """Test hook: fused conv1 + BN + ReLU + max pool on an S2D16 batch -> bf16 ``[n,56,56,64]``."""
+    l = _lib.lib()
+    n = int(x.shape[0])
+    out = torch.empty((n, 56, 56, 64), dtype=torch.bfloat16, device=x.device)
+    rc = l.hipac_resnet18_stem(packed.blob.data_ptr(), packed.num_classes, x.contiguous().data_ptr(), out.data_ptr(), n,
+                               torch.cuda.current_stream(x.device).cuda_stream)
+    _lib.check(rc, "hipac_resnet18_stem")
+    return out

@@ -131,3 +131,23 @@ def test_headless_packed_weights_and_errors():
     with pytest.raises(ValueError):
         features.extract_features_tensor(x.float(), packed)
     assert features.extract_features_tensor(x[:0], packed).shape == (0, 512)
+
+
+@pytest.mark.parametrize("n", [1, 2, 23])
+def test_fused_stem_vs_torch_fp32(net_and_packed, n):
+    """conv1 + folded BN + ReLU + 3x3/s2 max pool in one kernel vs torch on the same bf16 operands."""
+    from ss25_hierarchical_multiscale_image_classification_b200 import features
+    net, packed = net_and_packed
+    g = torch.Generator(device="cuda").manual_seed(n)
+    x = torch.randn((n, 224, 224, 3), generator=g, device="cuda").bfloat16()
+    w, b = _folded(net, 0)
+    conv = torch.relu(torch.nn.functional.conv2d(x.float().permute(0, 3, 1, 2), w, b, stride=2, padding=3))
+    ref = torch.nn.functional.max_pool2d(conv.bfloat16().float(), 3, 2, 1)       # kernel rounds to bf16 before pooling
+    xin = torch.zeros((n, 112, 115, 16), dtype=torch.bfloat16, device="cuda")
+    xin[:, :, 2:114, :12] = x.reshape(n, 112, 2, 112, 2, 3).permute(0, 1, 3, 2, 4, 5).reshape(n, 112, 112, 12)
+    out = features.stem(packed, xin)
+    torch.cuda.synchronize()
+    got = out.float().permute(0, 3, 1, 2)
+    scale = float(ref.abs().max())
+    err = float((got - ref).abs().max())
+    assert err <= 1.5 * 2.0 ** -8 * scale + 1e-3, f"stem: max err {err} at scale {scale}"
