@@ -19,6 +19,7 @@ HEADER = os.path.join(os.path.dirname(_HERE), "include", "hipac_b200.h")
 LAYOUT_NHWC3_BF16 = 1
 LAYOUT_S2D16_BF16 = 2
 SCAN_AUTO, SCAN_DIRECT, SCAN_FUSED = 0, 1, 2
+SCAN_KEEP_ALL = 0x100
 RESNET18_NUM_CONVS = 20
 
 _lock = threading.Lock()

@@ -141,7 +141,7 @@ __global__ void __launch_bounds__(256) k_stats_direct(ScanParams p, uint8_t* __r
 __global__ void __launch_bounds__(1024) k_compact(ScanParams p, const uint8_t* __restrict__ flags, int n_cand,
                                                   int32_t* __restrict__ coords, uint8_t* __restrict__ labels,
                                                   int32_t* __restrict__ src_idx, int32_t* __restrict__ count,
-                                                  int capacity) {
+                                                  int capacity, int keep_all) {
   __shared__ int warp_tot[32];
   __shared__ int base;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -150,7 +150,7 @@ __global__ void __launch_bounds__(1024) k_compact(ScanParams p, const uint8_t* _
   for (int start = 0; start < n_cand; start += 1024) {
     const int idx = start + threadIdx.x;
     const uint8_t f = idx < n_cand ? flags[idx] : 0;
-    const int keep = f & 1;
+    const int keep = idx < n_cand ? ((f & 1) | keep_all) : 0;
     const unsigned b = __ballot_sync(0xffffffffu, keep);
     const int pre = __popc(b & ((1u << lane) - 1));
     if (lane == 0) warp_tot[warp] = __popc(b);
@@ -320,6 +320,7 @@ static int scan_geometry(int H, int W, int P, int S, int iy_begin, int iy_end, i
 }
 
 extern "C" size_t hipac_tile_scan_workspace_bytes(int H, int W, int P, int S, int iy_begin, int iy_end, int mode) {
+  mode &= ~HIPAC_SCAN_KEEP_ALL;
   int nx, ny;
   if (scan_geometry(H, W, P, S, iy_begin, iy_end, &nx, &ny)) return 0;
   const size_t n_cand = (size_t)nx * ny;
@@ -337,6 +338,8 @@ extern "C" int hipac_tile_scan(const uint8_t* d_rgb, int H, int W, int64_t pitch
                                uint8_t* d_labels, uint8_t* d_batch_u8, void* d_batch, int layout, int32_t* d_count,
                                int capacity, void* d_workspace, size_t workspace_bytes, int mode, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
+  const int keep_all = (mode & HIPAC_SCAN_KEEP_ALL) ? 1 : 0;
+  mode &= ~HIPAC_SCAN_KEEP_ALL;
   int nx, ny;
   if (int e = scan_geometry(H, W, P, S, iy_begin, iy_end, &nx, &ny)) return e;
   HIPAC_REQUIRE(d_rgb && d_coords && d_labels && d_count && d_workspace, "null pointer");
@@ -372,7 +375,7 @@ extern "C" int hipac_tile_scan(const uint8_t* d_rgb, int H, int W, int64_t pitch
   HIPAC_REQUIRE(mode != HIPAC_SCAN_FUSED || fused_ok,
                 "fused scan needs stride % (P/224) == 0, gcd(stride, P) % 32 == 0 and a 16-byte aligned image");
   if (mode != HIPAC_SCAN_DIRECT && fused_ok) {
-    return fused_scan_impl(p, o, flags, src_idx, d_coords, d_labels, d_count, capacity, ws, stream);
+    return fused_scan_impl(p, o, flags, src_idx, d_coords, d_labels, d_count, capacity, ws, stream, keep_all);
   }
   {
     ProfileScope ps("stats_direct", stream, 0.0);
@@ -380,7 +383,7 @@ extern "C" int hipac_tile_scan(const uint8_t* d_rgb, int H, int W, int64_t pitch
   }
   {
     ProfileScope ps("compact", stream, (double)n_cand);
-    k_compact<<<1, 1024, 0, stream>>>(p, flags, n_cand, d_coords, d_labels, src_idx, d_count, capacity);
+    k_compact<<<1, 1024, 0, stream>>>(p, flags, n_cand, d_coords, d_labels, src_idx, d_count, capacity, keep_all);
   }
   count_launch(2);
   if ((d_batch_u8 || d_batch) && capacity > 0) {

@@ -421,7 +421,7 @@ static int launch_planes(const ScanParams& p, const FusedGeom& G, cudaStream_t s
 }
 
 static int fused_scan_impl(const ScanParams& p, const OutParams& o, uint8_t* flags, int32_t* src_idx, int32_t* d_coords,
-                           uint8_t* d_labels, int32_t* d_count, int capacity, uint8_t* ws, cudaStream_t stream) {
+                           uint8_t* d_labels, int32_t* d_count, int capacity, uint8_t* ws, cudaStream_t stream, int keep_all) {
   FusedGeom G;
   if (!fused_geometry(p, &G)) {
     set_error("fused scan not applicable to this stride / patch size");
@@ -450,7 +450,7 @@ static int fused_scan_impl(const ScanParams& p, const OutParams& o, uint8_t* fla
   }
   {
     ProfileScope ps("compact", stream, (double)n_cand);
-    k_compact<<<1, 1024, 0, stream>>>(p, flags, n_cand, d_coords, d_labels, src_idx, d_count, capacity);
+    k_compact<<<1, 1024, 0, stream>>>(p, flags, n_cand, d_coords, d_labels, src_idx, d_count, capacity, keep_all);
   }
   count_launch(3);
   if ((o.batch_u8 || o.batch) && capacity > 0) {

@@ -74,7 +74,7 @@ def read_level_rows(slide, level: int, y0: int, y1: int) -> np.ndarray:
     ds = slide.level_downsamples[level]
     width, _ = slide.level_dimensions[level]
     region = slide.read_region((0, int(y0 * ds)), level, (width, y1 - y0)).convert("RGB")
-    return np.asarray(region)
+    return np.array(region)   # own, writable copy (torch.from_numpy needs one)
 
 
 def scan_slide(slide, level: int, mask: np.ndarray | None, stride=None, patch_size: int = 224, device="cuda",
@@ -203,7 +203,7 @@ def extract_patches(patch_size=224, level=3, stride=None, pad=True, only_tumor=F
                      device, max_slab_bytes)
 
 
-def extract_patches_per_slide(slide_path, patch_size=224, level=3, stride=None, pad=True, only_tumor=False, *,
+def extract_patches_per_slide(slide_path="tumor_109", patch_size=224, level=3, stride=None, pad=True, only_tumor=False, *,
                               slide_opener=None, device="cuda", max_slab_bytes: int = 2 << 30):
     """Reference ``extract_patches_per_slide`` (``src/main.py:252-370``): same as ``extract_patches`` for one slide file."""
     cwd = os.getcwd()

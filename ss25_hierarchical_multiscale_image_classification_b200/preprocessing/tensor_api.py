@@ -58,13 +58,14 @@ def batch_shape(n: int, layout: str):
 def extract_patches_tensor(level_img: torch.Tensor, lesion_mask: torch.Tensor | None, level: int,
                            stride=None, row_range=None, patch_size: int = 224, layout: str | None = "s2d16",
                            want_u8: bool = False, mode: str = "auto", capacity: int | None = None,
-                           stream: torch.cuda.Stream | None = None) -> PatchBatch:
+                           stream: torch.cuda.Stream | None = None, keep_all: bool = False) -> PatchBatch:
     """Tile one level image (uint8 ``[H,W,3]`` on a CUDA device) exactly as the reference does.
 
     ``lesion_mask``: uint8 ``[H,W]`` (>0 = lesion, the rasterised ``parse_xml_mask`` output,
     reference ``src/main.py:372-410``) or ``None`` -> every patch "normal" (``src/main.py:714-716``).
     ``row_range=(i0,i1)`` restricts to candidate grid rows ``y//stride in [i0,i1)`` -- the
-    multi-GPU shard unit.  Synchronises once to read the survivor count.
+    multi-GPU shard unit.  ``keep_all`` disables the tissue rejection (used on stacks of already
+    extracted patches).  Synchronises once to read the survivor count.
     """
     l = _lib.lib()
     if not (level_img.is_cuda and level_img.dtype == torch.uint8 and level_img.dim() == 3 and level_img.shape[2] == 3):
@@ -93,7 +94,7 @@ def extract_patches_tensor(level_img: torch.Tensor, lesion_mask: torch.Tensor | 
         count = torch.zeros((2,), dtype=torch.int32, device=dev)
         batch = torch.empty(batch_shape(max(cap, 1), layout), dtype=torch.bfloat16, device=dev) if layout else None
         u8 = torch.empty((max(cap, 1), OUT, OUT, 3), dtype=torch.uint8, device=dev) if want_u8 else None
-        m = _MODES[mode]
+        m = _MODES[mode] | (_lib.SCAN_KEEP_ALL if keep_all else 0)
         ws_bytes = l.hipac_tile_scan_workspace_bytes(H, W, P, S, i0, i1, m)
         if ws_bytes == 0:
             raise RuntimeError("hipac_tile_scan_workspace_bytes: " + l.hipac_last_error().decode())
