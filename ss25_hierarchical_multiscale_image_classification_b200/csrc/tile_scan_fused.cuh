@@ -165,17 +165,21 @@ __global__ void __launch_bounds__(256) k_downsample_planes(ScanParams p, FusedGe
   constexpr int CI = plane_ci(F), RJ = plane_rj(F), IPT = plane_ipt(F), ROWCAP = plane_rowcap(F);
   constexpr int NI = 2 * F, NE = 3 * F / 2, HALF = F / 2;
   constexpr int SHIFT = F == 8 ? 7 : (F == 4 ? 5 : 3);  // interior weights are (2m+1) / 2^SHIFT exactly
+  constexpr int CH = ROWCAP / 16;                        // 16-byte chunks per staged row (upper bound)
+  static_assert(kPlaneG == 8 && 8 % F == 0, "stage rows must be a multiple of the scale");
   extern __shared__ __align__(16) uint8_t sm[];
   uint8_t* rows = sm;                                                       // [stages][G][ROWCAP]
   int* col_I = reinterpret_cast<int*>(sm + kPlaneStages * kPlaneG * ROWCAP);  // D column of each work column
   int* col_kind = col_I + (CI + 2 * (CI / 4 + 2));                          // 0 interior, 1 left, 2 right
+  constexpr int HB = 256 * IPT;                                             // bytes per row of the uint8 intermediate
+  uint8_t* hbuf = reinterpret_cast<uint8_t*>(col_kind + (CI + 2 * (CI / 4 + 2)));   // [G][HB]
   __shared__ int s_ncols;
 
   const int I0 = blockIdx.x * CI;
   const int Ja0 = G.Jbase + blockIdx.y * RJ;                // first D row owned by this CTA
   const int Ja1 = min(Ja0 + RJ, G.Jbase + G.Dh);
   const int Ib1 = min(I0 + CI, G.Dw);
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const CoeffSet& cs = c_coef[G.lf];
 
   // ---- work columns: interior columns of the band, then the ring-variant columns inside it ----
@@ -202,30 +206,56 @@ __global__ void __launch_bounds__(256) k_downsample_planes(ScanParams p, FusedGe
   const int nbytes = (px1c - px0c) * 3;
   const int64_t img_bytes = (int64_t)p.H * p.pitch;
   const int nstage_total = (rlast - rfirst + kPlaneG - 1) / kPlaneG;
+  // alignment phase of row r inside its first 16-byte chunk, in 32-bit arithmetic: (r*pitch + px0c*3) mod 16
+  const int pm = (int)(p.pitch & 15), pc = (px0c * 3) & 15;
+  const uint8_t* col0 = p.rgb + (int64_t)px0c * 3;
+  const bool edge_cols = px1 > px1c;
 
   auto issue_stage = [&](int st) {
     uint8_t* dst_stage = rows + (st % kPlaneStages) * kPlaneG * ROWCAP;
-    for (int rr = 0; rr < kPlaneG; rr++) {
-      const int r = rfirst + st * kPlaneG + rr;
-      if (r < 0 || r >= p.H || r >= rlast || nbytes <= 0) continue;
-      const int64_t start = (int64_t)r * p.pitch + (int64_t)px0c * 3;
-      const int64_t a0 = start & ~int64_t(15);
-      uint8_t* dst = dst_stage + rr * ROWCAP + kPlaneFront;  // dst[k] <-> global byte a0 + k
-      for (int64_t a = a0 + tid * 16; a < start + nbytes; a += 256 * 16) {
-        if (a + 16 <= img_bytes) {
-          cp_async_16(dst + (a - a0), p.rgb + a);
-        } else {
-          for (int b = 0; b < 16 && a + b < img_bytes; b++) dst[a - a0 + b] = p.rgb[a + b];
-        }
+    const int r0 = rfirst + st * kPlaneG;
+    for (int idx = tid; idx < kPlaneG * CH; idx += 256) {
+      const int rr = idx / CH, k = idx - rr * CH;
+      const int r = r0 + rr;
+      if (r < 0 || r >= p.H || r >= rlast) continue;
+      const int phase = (r * pm + pc) & 15;
+      if (k * 16 >= phase + nbytes) continue;
+      const uint8_t* src = col0 + (int64_t)r * p.pitch - phase + k * 16;   // 16-byte aligned
+      uint8_t* dst = dst_stage + rr * ROWCAP + kPlaneFront + k * 16;         // dst byte b <-> row byte b - phase
+      if (src + 16 <= p.rgb + img_bytes) {
+        cp_async_16(dst, src);
+      } else {
+        for (int b = 0; b < 16 && src + b < p.rgb + img_bytes; b++) dst[b] = src[b];
       }
     }
     cp_async_commit();
   };
 
-  // per-item state
+  // ---- per-item constants and state (items are fixed for the lifetime of the CTA) ----
   int A_int[IPT], A_top[IPT], A_bot[IPT], B_int[IPT], B_top[IPT], B_bot[IPT];
+  int it_off[IPT];        // col*3 + c inside hbuf, or -1
+  uint8_t* out_int[IPT];  // plane[0][hk] + ccol*3 + c  (row stride it_cw*3)
+  uint8_t* out_top[IPT];
+  uint8_t* out_bot[IPT];
+  int it_cw3[IPT];
 #pragma unroll
-  for (int q = 0; q < IPT; q++) A_int[q] = A_top[q] = A_bot[q] = B_int[q] = B_top[q] = B_bot[q] = 0;
+  for (int q = 0; q < IPT; q++) {
+    A_int[q] = A_top[q] = A_bot[q] = B_int[q] = B_top[q] = B_bot[q] = 0;
+    const int e = tid + q * 256;
+    it_off[q] = -1, out_int[q] = out_top[q] = out_bot[q] = nullptr, it_cw3[q] = 0;
+    if (e < nitems) {
+      const int c = e / ncols, col = e - c * ncols;
+      const int I = col_I[col], kind = col_kind[col];
+      const int ixv = kind == 1 ? I / G.Sf : (kind == 2 ? (I - (OUT - 1)) / G.Sf : 0);
+      const size_t ccol = kind == 0 ? (size_t)I : (size_t)ixv;
+      it_off[q] = col * 3 + c;
+      it_cw3[q] = (kind == 0 ? G.Dw : G.nx) * 3;
+      out_int[q] = G.plane[0][kind] + ccol * 3 + c;
+      out_top[q] = G.plane[1][kind] + ccol * 3 + c;
+      out_bot[q] = G.plane[2][kind] + ccol * 3 + c;
+    }
+  }
+  const int Sf = G.Sf, Jbase = G.Jbase, iy_begin = G.iy_begin, ny = G.ny, Himg = p.H;
 
   for (int st = 0; st < kPlaneStages - 1 && st < nstage_total; st++) issue_stage(st);
   for (int st = 0; st < nstage_total; st++) {
@@ -237,50 +267,90 @@ __global__ void __launch_bounds__(256) k_downsample_planes(ScanParams p, FusedGe
     }
     __syncthreads();
     uint8_t* stage = rows + (st % kPlaneStages) * kPlaneG * ROWCAP;
-    // white fill: rows outside the image, and pixels right of the image edge
-    for (int rr = 0; rr < kPlaneG; rr++) {
-      const int r = rfirst + st * kPlaneG + rr;
-      if (r >= rlast) break;
-      uint8_t* rowp = stage + rr * ROWCAP;
-      const int phase = (int)((((int64_t)(r < 0 ? 0 : r) * p.pitch + (int64_t)px0c * 3)) & 15);
-      if (r < 0 || r >= p.H) {
-        for (int k = tid; k < ROWCAP; k += 256) rowp[k] = 255;
-      } else if (px1 > px1c) {
-        for (int k = nbytes + tid; k < (px1 - px0c) * 3; k += 256) rowp[kPlaneFront + phase + k] = 255;
+    const int r_stage = rfirst + st * kPlaneG;
+    const int nrows = min(kPlaneG, rlast - r_stage);
+    // white fill: rows outside the image, and pixels right of the image edge (edge CTAs only; CTA-uniform test)
+    if (r_stage < 0 || r_stage + nrows > Himg || edge_cols) {
+      for (int rr = 0; rr < nrows; rr++) {
+        const int r = r_stage + rr;
+        uint8_t* rowp = stage + rr * ROWCAP;
+        if (r < 0 || r >= Himg) {
+          for (int k = tid; k < ROWCAP; k += 256) rowp[k] = 255;
+        } else if (edge_cols) {
+          const int phase = (r * pm + pc) & 15;
+          for (int k = nbytes + tid; k < (px1 - px0c) * 3; k += 256) rowp[kPlaneFront + phase + k] = 255;
+        }
+      }
+      __syncthreads();
+    }
+    // ---- horizontal pass: warp w <-> stage row w, lanes stride over the work columns, 3 channels per item ----
+    if (warp < nrows) {
+      const int r = r_stage + warp;
+      const uint8_t* rowp = stage + warp * ROWCAP;
+      const int phase = (r < 0 || r >= Himg) ? 0 : ((r * pm + pc) & 15);
+      uint8_t* hrow = hbuf + warp * HB;
+      for (int col = lane; col < ncols; col += 32) {
+        const int I = col_I[col], kind = col_kind[col];
+        uint8_t* hout = hrow + col * 3;
+        if (kind == 0) {
+          // 2F taps x 3 interleaved channels = 6F bytes: word loads, funnel-shift to the window start, PRMT the
+          // stride-3 bytes of each channel into one register, dp4a with the (2m+1) weights (exact: the weights are
+          // (2m+1)/2^SHIFT, so Pillow's 22-bit fixed point reduces to (T + 2^(SHIFT-1)) >> SHIFT)
+          const int A = kPlaneFront + phase + (F * I - HALF - px0c) * 3;   // >= 4: the front pad absorbs I == 0
+          const uint32_t* wp = reinterpret_cast<const uint32_t*>(rowp) + (A >> 2);
+          const uint32_t sh = (A & 3) * 8;
+          constexpr int NW = 6 * F / 4;
+          uint32_t wd[NW + 1];
+#pragma unroll
+          for (int k = 0; k <= NW; k++) wd[k] = wp[k];
+#pragma unroll
+          for (int k = 0; k < NW; k++) wd[k] = __funnelshift_r(wd[k], wd[k + 1], sh);
+          uint32_t T0 = 0, T1 = 0, T2 = 0;
+#pragma unroll
+          for (int q = 0; q < NI / 4; q++) {
+            uint32_t wt = 0;
+#pragma unroll
+            for (int jj = 0; jj < 4; jj++) {
+              const int t = 4 * q + jj;
+              wt |= (uint32_t)(t < F ? 2 * t + 1 : 2 * (NI - 1 - t) + 1) << (8 * jj);
+            }
+            const uint32_t a = wd[3 * q], b = wd[3 * q + 1], cc = wd[3 * q + 2];
+            T0 = __dp4a(__byte_perm(__byte_perm(a, b, 0x0630), cc, 0x5210), wt, T0);
+            T1 = __dp4a(__byte_perm(__byte_perm(a, b, 0x0741), cc, 0x6210), wt, T1);
+            T2 = __dp4a(__byte_perm(__byte_perm(a, b, 0x0052), cc, 0x7410), wt, T2);
+          }
+          hout[0] = (uint8_t)((T0 + (1u << (SHIFT - 1))) >> SHIFT);
+          hout[1] = (uint8_t)((T1 + (1u << (SHIFT - 1))) >> SHIFT);
+          hout[2] = (uint8_t)((T2 + (1u << (SHIFT - 1))) >> SHIFT);
+        } else {
+          const uint8_t* pix = rowp + kPlaneFront + phase + (kind == 1 ? F * I - px0c : F * I - HALF - px0c) * 3;
+          const int32_t* kh = kind == 1 ? cs.left : cs.right;
+          int a0 = 1 << (kPrecisionBits - 1), a1 = a0, a2 = a0;
+#pragma unroll
+          for (int t = 0; t < NE; t++) {
+            a0 += kh[t] * (int)pix[3 * t], a1 += kh[t] * (int)pix[3 * t + 1], a2 += kh[t] * (int)pix[3 * t + 2];
+          }
+          hout[0] = (uint8_t)min(max(a0 >> kPrecisionBits, 0), 255);
+          hout[1] = (uint8_t)min(max(a1 >> kPrecisionBits, 0), 255);
+          hout[2] = (uint8_t)min(max(a2 >> kPrecisionBits, 0), 255);
+        }
       }
     }
     __syncthreads();
+    // ---- vertical pass.  Stage row rr is image row r_stage + rr with (r + HALF) = F * (Ja0 + (8*st + rr) / F) + rr % F,
+    //      so the tap index tb = rr % F is a compile-time constant of the unrolled loop. ----
+    const int Jstage = Ja0 + (kPlaneG / F) * st;   // D row whose window starts at stage row 0
 #pragma unroll
     for (int q = 0; q < IPT; q++) {
-      const int e = tid + q * 256;
-      if (e >= nitems) continue;
-      const int c = e / ncols, col = e - c * ncols;
-      const int I = col_I[col], kind = col_kind[col];
+      if (it_off[q] < 0) continue;
+      const uint8_t* hp = hbuf + it_off[q];
+#pragma unroll
       for (int rr = 0; rr < kPlaneG; rr++) {
-        const int r = rfirst + st * kPlaneG + rr;
-        if (r >= rlast) break;
-        const uint8_t* rowp = stage + rr * ROWCAP;
-        const int phase = (int)((((int64_t)((r < 0 || r >= p.H) ? 0 : r) * p.pitch + (int64_t)px0c * 3)) & 15);
-        // byte k of the logical row (pixel px0c + k/3) sits at rowp[kPlaneFront + phase + k]
-        const uint8_t* pix = rowp + kPlaneFront + ((r < 0 || r >= p.H) ? 0 : phase) + c;
-        int h;
-        if (kind == 0) {
-          const int b0 = (F * I - HALF - px0c) * 3;  // may be negative for I == 0 (value unused; stays in the front pad)
-          int T = 0;
-#pragma unroll
-          for (int t = 0; t < NI; t++) T += (t < F ? 2 * t + 1 : 2 * (NI - 1 - t) + 1) * (int)pix[b0 + 3 * t];
-          h = (T + (1 << (SHIFT - 1))) >> SHIFT;
-        } else {
-          const int b0 = (kind == 1 ? F * I - px0c : F * I - HALF - px0c) * 3;
-          const int32_t* kh = kind == 1 ? cs.left : cs.right;
-          int acc = 1 << (kPrecisionBits - 1);
-#pragma unroll
-          for (int t = 0; t < NE; t++) acc += kh[t] * (int)pix[b0 + 3 * t];
-          h = min(max(acc >> kPrecisionBits, 0), 255);
-        }
-        // ---- vertical accumulation: image row r feeds D rows Jb (tap tb) and Jb-1 (tap tb+F) ----
-        const int d = r + HALF;
-        const int Jb = d / F, tb = d - Jb * F;
+        if (rr >= nrows) break;
+        constexpr int kDummy = 0;
+        (void)kDummy;
+        const int tb = rr % F;
+        const int h = hp[rr * HB];
         B_int[q] += (2 * tb + 1) * h;
         A_int[q] += (2 * (F - 1 - tb) + 1) * h;
         B_bot[q] += cs.right[tb] * h;
@@ -288,24 +358,18 @@ __global__ void __launch_bounds__(256) k_downsample_planes(ScanParams p, FusedGe
         if (tb >= HALF) B_top[q] += cs.left[tb - HALF] * h;
         A_top[q] += cs.left[tb + HALF] * h;
         if (tb == F - 1) {
-          const int J = Jb - 1;
+          const int J = Jstage + rr / F - 1;       // the D row that just received its last tap
           if (J >= Ja0 && J < Ja1) {
-            const int hk = kind;
-            const int ixv = kind == 1 ? I / G.Sf : (kind == 2 ? (I - (OUT - 1)) / G.Sf : 0);
-            const size_t ccol = hk == 0 ? (size_t)I : (size_t)ixv;
-            const size_t cw = hk == 0 ? (size_t)G.Dw : (size_t)G.nx;
-            G.plane[0][hk][((size_t)(J - G.Jbase) * cw + ccol) * 3 + c] = (uint8_t)((A_int[q] + (1 << (SHIFT - 1))) >> SHIFT);
-            if (J % G.Sf == 0) {
-              const int iy = J / G.Sf - G.iy_begin;
-              if (iy >= 0 && iy < G.ny)
-                G.plane[1][hk][((size_t)iy * cw + ccol) * 3 + c] =
-                    (uint8_t)min(max((A_top[q] + (1 << (kPrecisionBits - 1))) >> kPrecisionBits, 0), 255);
+            out_int[q][(size_t)(J - Jbase) * it_cw3[q]] = (uint8_t)((A_int[q] + (1 << (SHIFT - 1))) >> SHIFT);
+            if (J % Sf == 0) {
+              const int iy = J / Sf - iy_begin;
+              if (iy >= 0 && iy < ny)
+                out_top[q][(size_t)iy * it_cw3[q]] = (uint8_t)min(max((A_top[q] + (1 << (kPrecisionBits - 1))) >> kPrecisionBits, 0), 255);
             }
-            if (J >= OUT - 1 && (J - (OUT - 1)) % G.Sf == 0) {
-              const int iy = (J - (OUT - 1)) / G.Sf - G.iy_begin;
-              if (iy >= 0 && iy < G.ny)
-                G.plane[2][hk][((size_t)iy * cw + ccol) * 3 + c] =
-                    (uint8_t)min(max((A_bot[q] + (1 << (kPrecisionBits - 1))) >> kPrecisionBits, 0), 255);
+            if (J >= OUT - 1 && (J - (OUT - 1)) % Sf == 0) {
+              const int iy = (J - (OUT - 1)) / Sf - iy_begin;
+              if (iy >= 0 && iy < ny)
+                out_bot[q][(size_t)iy * it_cw3[q]] = (uint8_t)min(max((A_bot[q] + (1 << (kPrecisionBits - 1))) >> kPrecisionBits, 0), 255);
             }
           }
           A_int[q] = B_int[q], A_top[q] = B_top[q], A_bot[q] = B_bot[q];
@@ -313,55 +377,96 @@ __global__ void __launch_bounds__(256) k_downsample_planes(ScanParams p, FusedGe
         }
       }
     }
-    __syncthreads();
   }
 }
 
 // ------------------------------------------------------------------------------------------
-// pass B: gather the 224 x 224 crop of every survivor from the planes (or the image when f == 1)
-//   grid (survivor slot, 14 groups of 8 row pairs); the 16 plane rows are staged in shared memory, then
-//   thread X of a row pair produces the 2x2 output pixels (2*jp+dy, 2*X+dx) -- exactly one 32-byte
-//   space-to-depth pixel of the conv1 operand.
-// ------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t fused_fetch(const ScanParams& p, const FusedGeom& G, int x, int y, int iyl, int j,
-                                                int i, int c) {
+constexpr int kGatherPairs = 8;                 // output row pairs per CTA (112 = 14 * 8)
+constexpr int kGatherRowCap = OUT * 3 + 16;     // 672 row bytes + alignment phase, multiple of 16
+
+// Source of output row j of a patch: pointer to the 672 contiguous bytes of its interior columns (or null when the
+// whole row is white), number of valid leading bytes, and the two ring pixels that come from the clamp planes.
+struct GatherRow {
+  const uint8_t* src;     // byte 0 = output column 0 (interior plane / image row), may be unaligned
+  int valid;              // bytes [0, valid) exist in the source; the rest is white (255)
+  const uint8_t* left;    // 3 bytes for output column 0, or null (use src)
+  const uint8_t* right;   // 3 bytes for output column 223, or null (use src)
+};
+
+__device__ __forceinline__ GatherRow gather_row(const ScanParams& p, const FusedGeom& G, int x, int y, int iyl, int j) {
+  GatherRow g;
+  g.left = g.right = nullptr;
   if (G.f == 1) {
-    const int yy = y + j, xx = x + i;
-    return (yy < p.H && xx < p.W) ? p.rgb[(int64_t)yy * p.pitch + (int64_t)xx * 3 + c] : 255u;
+    const int yy = y + j;
+    g.src = yy < p.H ? p.rgb + (int64_t)yy * p.pitch + (int64_t)x * 3 : nullptr;
+    g.valid = yy < p.H ? min(OUT, p.W - x) * 3 : 0;
+    return g;
   }
-  const int J = y / G.f + j - G.Jbase, I = x / G.f + i;
-  if (J >= G.Dh || I >= G.Dw) return 255u;  // window entirely in the white padding
-  const int vk = j == 0 ? 1 : (j == OUT - 1 ? 2 : 0), hk = i == 0 ? 1 : (i == OUT - 1 ? 2 : 0);
+  const int J = y / G.f + j - G.Jbase, I0 = x / G.f;
+  if (J >= G.Dh) {  // vertical window entirely in the white padding
+    g.src = nullptr, g.valid = 0;
+    return g;
+  }
+  const int vk = j == 0 ? 1 : (j == OUT - 1 ? 2 : 0);
   const size_t row = vk == 0 ? (size_t)J : (size_t)iyl;
-  const size_t cw = hk == 0 ? (size_t)G.Dw : (size_t)G.nx;
-  const size_t col = hk == 0 ? (size_t)I : (size_t)(x / p.S);
-  return G.plane[vk][hk][(row * cw + col) * 3 + c];
+  g.src = G.plane[vk][0] + (row * G.Dw + I0) * 3;
+  g.valid = max(0, min(OUT, G.Dw - I0)) * 3;
+  const size_t ix = (size_t)(x / p.S);
+  g.left = G.plane[vk][1] + (row * G.nx + ix) * 3;                       // column I0 always exists (x < W)
+  g.right = I0 + OUT - 1 < G.Dw ? G.plane[vk][2] + (row * G.nx + ix) * 3 : nullptr;   // else white via `valid`
+  return g;
 }
 
-constexpr int kGatherPairs = 8;  // output row pairs per CTA (112 = 14 * 8)
-
+// pass B: gather the 224 x 224 crop of every survivor from the planes (or the image when f == 1).
+//   grid (survivor slot, 14 groups of 8 row pairs).  Each warp copies whole source rows into shared memory with
+//   aligned 32-bit loads (the row keeps its global alignment phase), patches the two ring pixels, then thread X
+//   of a row pair produces the 2x2 output pixels (2*jp+dy, 2*X+dx) = one 32-byte space-to-depth pixel.
 __global__ void __launch_bounds__(128) k_gather(ScanParams p, FusedGeom G, OutParams o, const int32_t* __restrict__ coords,
                                                 const int32_t* __restrict__ count, int capacity) {
   const int slot = blockIdx.x, jp0 = blockIdx.y * kGatherPairs;
   if (slot >= min(count[0], capacity)) return;
-  __shared__ __align__(16) uint8_t rowbuf[2 * kGatherPairs][OUT * 3];
+  __shared__ __align__(16) uint8_t rowbuf[2 * kGatherPairs][kGatherRowCap];
+  __shared__ int rowphase[2 * kGatherPairs];
   __shared__ uint16_t lut[768];
   const int x = coords[2 * slot], y = coords[2 * slot + 1];
   const int iyl = y / p.S - p.iy_begin;
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   for (int e = tid; e < 384; e += 128) reinterpret_cast<uint32_t*>(lut)[e] = reinterpret_cast<const uint32_t*>(g_lut_bf16)[e];
-  // stage 16 output rows (672 contiguous plane bytes each) with coalesced byte loads
-  for (int e = tid; e < 2 * kGatherPairs * OUT * 3; e += 128) {
-    const int rr = e / (OUT * 3), k = e - rr * (OUT * 3);
-    const int i = k / 3, c = k - 3 * i;
-    rowbuf[rr][k] = (uint8_t)fused_fetch(p, G, x, y, iyl, 2 * jp0 + rr, i, c);
+  for (int rr = warp; rr < 2 * kGatherPairs; rr += 4) {
+    const GatherRow g = gather_row(p, G, x, y, iyl, 2 * jp0 + rr);
+    const int phase = g.src ? (int)(reinterpret_cast<uintptr_t>(g.src) & 3) : 0;
+    uint32_t* dst = reinterpret_cast<uint32_t*>(rowbuf[rr]);
+    const int nwords = (phase + g.valid + 3) >> 2;                       // aligned words covering the valid bytes
+    const uint32_t* srcw = reinterpret_cast<const uint32_t*>(g.src - phase);
+    // words that would cross the end of the level image (only possible for f == 1, last row) are assembled bytewise
+    const uint8_t* img_end = p.rgb + (int64_t)p.H * p.pitch;
+    for (int k = lane; k < kGatherRowCap / 4; k += 32) {
+      uint32_t v = 0xFFFFFFFFu;
+      if (k < nwords) {
+        const uint8_t* a = reinterpret_cast<const uint8_t*>(srcw + k);
+        if (G.f != 1 || a + 4 <= img_end) {
+          v = __ldg(srcw + k);
+        } else {
+          v = 0;
+          for (int b = 0; b < 4 && a + b < img_end; b++) v |= (uint32_t)a[b] << (8 * b);
+        }
+      }
+      dst[k] = v;
+    }
+    __syncwarp();
+    uint8_t* row = rowbuf[rr] + phase;
+    for (int k = g.valid + lane; k < OUT * 3 && k < g.valid + 4; k += 32) row[k] = 255;   // tail of the last word
+    if (lane < 3 && g.left) row[lane] = g.left[lane];
+    if (lane < 3 && g.right) row[(OUT - 1) * 3 + lane] = g.right[lane];
+    if (lane == 0) rowphase[rr] = phase;
   }
   __syncthreads();
   const int X = tid;
   if (o.batch_u8) {
     for (int rr = 0; rr < 2 * kGatherPairs; rr++) {
       uint8_t* dst = o.batch_u8 + (((int64_t)slot * OUT + 2 * jp0 + rr) * OUT) * 3;
-      for (int k = tid; k < OUT * 3; k += 128) dst[k] = rowbuf[rr][k];
+      const uint8_t* row = rowbuf[rr] + rowphase[rr];
+      for (int k = tid; k < OUT * 3; k += 128) dst[k] = row[k];
     }
   }
   if (!o.batch) return;
@@ -379,14 +484,14 @@ __global__ void __launch_bounds__(128) k_gather(ScanParams p, FusedGeom G, OutPa
     }
 #pragma unroll 2
     for (int q = 0; q < kGatherPairs; q++) {
+      const uint8_t* r0 = rowbuf[2 * q] + rowphase[2 * q] + 6 * X;        // 2 pixels x 3 channels of the even row
+      const uint8_t* r1 = rowbuf[2 * q + 1] + rowphase[2 * q + 1] + 6 * X;
       uint32_t w[8];
 #pragma unroll
-      for (int k = 0; k < 6; k++) {
-        // channel index ch = (dy*2+dx)*3+c of the 32-byte space-to-depth pixel; two channels per word
-        const int e0 = 2 * k, e1 = 2 * k + 1;
-        const uint32_t v0 = rowbuf[2 * q + e0 / 6][(2 * X + ((e0 / 3) & 1)) * 3 + e0 % 3];
-        const uint32_t v1 = rowbuf[2 * q + e1 / 6][(2 * X + ((e1 / 3) & 1)) * 3 + e1 % 3];
-        w[k] = (uint32_t)lut[v0 * 3 + e0 % 3] | ((uint32_t)lut[v1 * 3 + e1 % 3] << 16);
+      for (int k = 0; k < 3; k++) {
+        // s2d channel (dy*2+dx)*3+c = dy*6 + (dx*3+c): the 6 bytes of a row are already in channel order
+        w[k] = (uint32_t)lut[r0[2 * k] * 3 + (2 * k) % 3] | ((uint32_t)lut[r0[2 * k + 1] * 3 + (2 * k + 1) % 3] << 16);
+        w[3 + k] = (uint32_t)lut[r1[2 * k] * 3 + (2 * k) % 3] | ((uint32_t)lut[r1[2 * k + 1] * 3 + (2 * k + 1) % 3] << 16);
       }
       w[6] = w[7] = 0;
       uint4* dst = reinterpret_cast<uint4*>(o.batch + ((((int64_t)slot * (OUT / 2) + jp0 + q) * HIPAC_S2D16_WIDTH + X + 2) << 4));
@@ -396,7 +501,8 @@ __global__ void __launch_bounds__(128) k_gather(ScanParams p, FusedGeom G, OutPa
   } else {
     for (int rr = 0; rr < 2 * kGatherPairs; rr++) {
       uint16_t* dst = o.batch + (((int64_t)slot * OUT + 2 * jp0 + rr) * OUT) * 3;
-      for (int k = tid; k < OUT * 3; k += 128) dst[k] = lut[rowbuf[rr][k] * 3 + k % 3];
+      const uint8_t* row = rowbuf[rr] + rowphase[rr];
+      for (int k = tid; k < OUT * 3; k += 128) dst[k] = lut[row[k] * 3 + k % 3];
     }
   }
 }
@@ -407,7 +513,8 @@ __global__ void __launch_bounds__(128) k_gather(ScanParams p, FusedGeom G, OutPa
 template <int F>
 static int launch_planes(const ScanParams& p, const FusedGeom& G, cudaStream_t stream) {
   constexpr int CI = plane_ci(F), RJ = plane_rj(F);
-  const size_t smem = (size_t)kPlaneStages * kPlaneG * plane_rowcap(F) + 2 * (CI + 2 * (CI / 4 + 2)) * sizeof(int);
+  const size_t smem = (size_t)kPlaneStages * kPlaneG * plane_rowcap(F) + 2 * (CI + 2 * (CI / 4 + 2)) * sizeof(int) +
+                      (size_t)kPlaneG * 256 * plane_ipt(F);
   static bool attr = false;
   if (!attr) {
     HIPAC_CHECK_CUDA(cudaFuncSetAttribute(k_downsample_planes<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
