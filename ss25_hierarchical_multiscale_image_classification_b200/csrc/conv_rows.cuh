@@ -39,7 +39,7 @@ struct RowCfg {
 };
 
 template <int BN, int KC, int W, int R, bool RESIDENT>
-__global__ void __launch_bounds__(kConvThreads, 1)
+__global__ void __launch_bounds__(conv_threads(BN), 1)
 k_conv3x3_rows(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const RowConvParams p) {
   using Cfg = RowCfg<BN, KC, W, R, RESIDENT>;
   constexpr int Wp = Cfg::Wp, H = W, TILES_PER_IMG = H / R;
@@ -167,8 +167,11 @@ k_conv3x3_rows(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int pos = wq * 32 + lane;          // position in the padded-width tile
     const int rr = pos / Wp, x = pos - rr * Wp;
     const bool valid = rr < R && x < W;
-    uint32_t acc = 0, acc_phase = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+    const int grp = (warp - 2) >> 2;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      if (epi_groups(BN) == 2 && (it & 1) != grp) continue;
+      const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
       const int img = tile / TILES_PER_IMG, p0 = (tile - img * TILES_PER_IMG) * R;
       const size_t pix = ((size_t)img * H + p0 + rr) * W + x;
       epilogue_row<BN>(tmem_base + ((uint32_t)(wq * 32) << 16) + acc * BN, p.bias, p.residual ? p.residual + pix * BN : nullptr,
@@ -176,8 +179,6 @@ k_conv3x3_rows(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&tempty[acc]);
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1;
     }
   }
   ptx::tc_fence_before();

@@ -41,7 +41,9 @@ __device__ __forceinline__ uint4 bf16x8_max(uint4 a, uint4 b) {
   return r;
 }
 
-__global__ void __launch_bounds__(kConvThreads, 1)
+constexpr int kStemThreads = 64 + 256;  // producer warp, MMA warp, 8 epilogue warps (2 per TMEM lane quarter: 32 channels each)
+
+__global__ void __launch_bounds__(kStemThreads, 1)
 k_conv1_pool(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const StemParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -61,7 +63,7 @@ k_conv1_pool(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     ptx::prefetch_tensormap(&tmB);
     for (int s = 0; s < 2; s++) ptx::mbar_init(&a_full[s], 1), ptx::mbar_init(&a_empty[s], 1);
     ptx::mbar_init(w_full, 1);
-    for (int a = 0; a < 2; a++) ptx::mbar_init(&tfull[a], 1), ptx::mbar_init(&tempty[a], 4);
+    for (int a = 0; a < 2; a++) ptx::mbar_init(&tfull[a], 1), ptx::mbar_init(&tempty[a], 8);
     ptx::fence_barrier_init();
   }
   if (warp == 1) {
@@ -128,9 +130,10 @@ k_conv1_pool(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     }
   } else {
     // ===================== epilogue: bias + ReLU -> running max -> pooled row =====================
-    const int wq = warp & 3;
-    const int x = wq * 32 + lane;  // conv column of this thread's accumulator row
-    const int et = threadIdx.x - 64;  // 0..127 among the epilogue threads
+    // 8 warps: warp (2 + 4*half + wq) owns TMEM lanes 32*wq.. and channels 32*half..32*half+31 of every conv row.
+    const int wq = warp & 3, half = (warp - 2) >> 2;
+    const int x = wq * 32 + lane;          // conv column of this thread's accumulator row
+    const int et = threadIdx.x - 64;       // 0..255 among the epilogue threads
     const bool valid = x < 112;
     uint32_t acc = 0, acc_phase = 0;
     for (int blk = blockIdx.x; blk < p.num_blocks; blk += gridDim.x) {
@@ -140,62 +143,58 @@ k_conv1_pool(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         const bool closes = t > 0 && (t & 1) == 0;    // conv row 2*py + 1: pooled row py = py0 + t/2 - 1 is complete
         ptx::mbar_wait(&tfull[acc], acc_phase);
         ptx::tc_fence_after();
-        uint32_t v0[32], v1[32];
-        ptx::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(wq * 32) << 16) + acc * 64, v0);
-        ptx::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(wq * 32) << 16) + acc * 64 + 32, v1);
+        uint32_t v[32];
+        ptx::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(wq * 32) << 16) + acc * 64 + half * 32, v);
         ptx::tmem_ld_wait();
         ptx::tc_fence_before();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&tempty[acc]);   // accumulator drained into registers
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
-        uint4 cur[8];  // this pixel's 64 channels, bf16
+        uint4 cur[4];  // this pixel's 32 channels, bf16
 #pragma unroll
-        for (int i = 0; i < 16; i++) {
-          const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias) + i);
-          const uint32_t* src = i < 8 ? &v0[4 * i] : &v1[4 * (i - 8)];
-          const float y0 = fmaxf(__uint_as_float(src[0]) + b.x, 0.f), y1 = fmaxf(__uint_as_float(src[1]) + b.y, 0.f);
-          const float y2 = fmaxf(__uint_as_float(src[2]) + b.z, 0.f), y3 = fmaxf(__uint_as_float(src[3]) + b.w, 0.f);
+        for (int i = 0; i < 8; i++) {
+          const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + half * 32) + i);
+          const float y0 = fmaxf(__uint_as_float(v[4 * i + 0]) + b.x, 0.f), y1 = fmaxf(__uint_as_float(v[4 * i + 1]) + b.y, 0.f);
+          const float y2 = fmaxf(__uint_as_float(v[4 * i + 2]) + b.z, 0.f), y3 = fmaxf(__uint_as_float(v[4 * i + 3]) + b.w, 0.f);
           __nv_bfloat162 lo = __floats2bfloat162_rn(y0, y1), hi = __floats2bfloat162_rn(y2, y3);
           uint32_t* dst = reinterpret_cast<uint32_t*>(&cur[i >> 1]) + (i & 1) * 2;
           dst[0] = *reinterpret_cast<uint32_t*>(&lo);
           dst[1] = *reinterpret_cast<uint32_t*>(&hi);
         }
+        uint4* mine = reinterpret_cast<uint4*>(sV + x * 128);
         if (valid) {
-          uint4* mine = reinterpret_cast<uint4*>(sV + x * 128);
 #pragma unroll
-          for (int j = 0; j < 8; j++) {
-            const int jj = j ^ (x & 7);  // XOR swizzle: conflict-free 16-byte accesses at a 128-byte row stride
+          for (int j = 0; j < 4; j++) {
+            const int jj = (half * 4 + j) ^ (x & 7);  // XOR swizzle: conflict-free 16-byte accesses at a 128-byte row stride
             mine[jj] = init ? cur[j] : bf16x8_max(mine[jj], cur[j]);
           }
         }
         if (closes) {
           // the running max is complete: horizontal 3-max, then restart it from this (shared) odd conv row
-          named_bar_sync(1, 128);
-          if (et < 112) {
-            // thread -> (pooled column px, channel half): 3-max over conv columns 2px-1, 2px, 2px+1
-            const int px = et >> 1, half = et & 1;
+          named_bar_sync(1, 256);
+          if (et < 224) {
+            // thread -> (pooled column px, 16-channel quarter): 3-max over conv columns 2px-1, 2px, 2px+1
+            const int px = et >> 2, qtr = et & 3;
             const int py = py0 + (t >> 1) - 1;
-            uint4 m[4];
+            uint4 m[2];
 #pragma unroll
-            for (int j = 0; j < 4; j++) m[j] = reinterpret_cast<const uint4*>(sV + (2 * px) * 128)[(half * 4 + j) ^ ((2 * px) & 7)];
+            for (int j = 0; j < 2; j++) m[j] = reinterpret_cast<const uint4*>(sV + (2 * px) * 128)[(qtr * 2 + j) ^ ((2 * px) & 7)];
             if (px > 0) {
 #pragma unroll
-              for (int j = 0; j < 4; j++)
-                m[j] = bf16x8_max(m[j], reinterpret_cast<const uint4*>(sV + (2 * px - 1) * 128)[(half * 4 + j) ^ ((2 * px - 1) & 7)]);
+              for (int j = 0; j < 2; j++)
+                m[j] = bf16x8_max(m[j], reinterpret_cast<const uint4*>(sV + (2 * px - 1) * 128)[(qtr * 2 + j) ^ ((2 * px - 1) & 7)]);
             }
 #pragma unroll
-            for (int j = 0; j < 4; j++)
-              m[j] = bf16x8_max(m[j], reinterpret_cast<const uint4*>(sV + (2 * px + 1) * 128)[(half * 4 + j) ^ ((2 * px + 1) & 7)]);
-            uint4* dst = reinterpret_cast<uint4*>(p.out + (((size_t)img * 56 + py) * 56 + px) * 64 + half * 32);
-#pragma unroll
-            for (int j = 0; j < 4; j++) dst[j] = m[j];
+            for (int j = 0; j < 2; j++)
+              m[j] = bf16x8_max(m[j], reinterpret_cast<const uint4*>(sV + (2 * px + 1) * 128)[(qtr * 2 + j) ^ ((2 * px + 1) & 7)]);
+            uint4* dst = reinterpret_cast<uint4*>(p.out + (((size_t)img * 56 + py) * 56 + px) * 64 + qtr * 16);
+            dst[0] = m[0], dst[1] = m[1];
           }
-          named_bar_sync(1, 128);  // everyone has read its neighbours' columns
+          named_bar_sync(1, 256);  // everyone has read its neighbours' columns
           if (valid) {
-            uint4* mine = reinterpret_cast<uint4*>(sV + x * 128);
 #pragma unroll
-            for (int j = 0; j < 8; j++) mine[j ^ (x & 7)] = cur[j];
+            for (int j = 0; j < 4; j++) mine[(half * 4 + j) ^ (x & 7)] = cur[j];
           }
         }
       }

@@ -40,6 +40,10 @@ constexpr int kBM = 128;
 constexpr int kS2dW = HIPAC_S2D16_WIDTH;  // 112 + 3 explicit zero columns (2 left, 1 right)
 constexpr int kABytes = kBM * 128;  // 128 rows x 64 bf16
 constexpr int kConvThreads = 192;   // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
+// 64-wide tiles have so little MMA work per tile that one epilogue warpgroup cannot keep up: they get two, which
+// take alternate tiles (= alternate TMEM accumulator buffers).  Wider tiles keep one (register budget).
+__host__ __device__ constexpr int epi_groups(int bn) { return bn == 64 ? 2 : 1; }
+__host__ __device__ constexpr int conv_threads(int bn) { return 64 + 128 * epi_groups(bn); }
 
 // 32 consecutive output channels of one output pixel: + folded-BN bias (+ residual, already in registers)
 // (+ ReLU) -> bf16, 64-byte store.
@@ -114,7 +118,7 @@ struct ConvCfg {
 };
 
 template <int BN>
-__global__ void __launch_bounds__(kConvThreads, 1)
+__global__ void __launch_bounds__(conv_threads(BN), 1)
 k_conv_umma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvParams p) {
   using Cfg = ConvCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
@@ -207,8 +211,11 @@ k_conv_umma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     // ===================== epilogue: TMEM -> +bias (+residual) -> ReLU -> bf16 NHWC =====================
     const int wq = warp & 3;  // TMEM lane quarter this warp may access
     const int row = wq * 32 + lane;
-    uint32_t acc = 0, acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    const int grp = (warp - 2) >> 2;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      if (epi_groups(BN) == 2 && (it & 1) != grp) continue;
+      const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
       const int m_tile = tile / p.num_n_tiles, n_tile = tile - m_tile * p.num_n_tiles;
       const int m = m_tile * kBM + row;
       const bool valid = m < p.M_total;
@@ -220,8 +227,6 @@ k_conv_umma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&tempty[acc]);
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1;
     }
   }
 
@@ -437,7 +442,7 @@ static int launch_rows_t(const uint8_t* d_packed, const PackedLayout& L, int lay
   const int grid = p.num_tiles < g_num_sms ? p.num_tiles : g_num_sms;
   {
     ProfileScope ps(name, stream, 2.0 * n * W * W * BN * 9 * KC * 64);
-    k_conv3x3_rows<BN, KC, W, R, RESIDENT><<<grid, kConvThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, p);
+    k_conv3x3_rows<BN, KC, W, R, RESIDENT><<<grid, conv_threads(BN), Cfg::kSmemBytes, stream>>>(tmA, tmB, p);
   }
   count_launch(1);
   HIPAC_CHECK_CUDA(cudaGetLastError());
@@ -473,7 +478,7 @@ static int run_stem(const uint8_t* d_packed, const PackedLayout& L, const void* 
   const int grid = p.num_blocks < g_num_sms ? p.num_blocks : g_num_sms;
   {
     ProfileScope ps("conv1_pool_fused", stream, 2.0 * n * 112 * 112 * 64 * 147);
-    k_conv1_pool<<<grid, kConvThreads, kStemSmem, stream>>>(tmA, tmB, p);
+    k_conv1_pool<<<grid, kStemThreads, kStemSmem, stream>>>(tmA, tmB, p);
   }
   count_launch(1);
   HIPAC_CHECK_CUDA(cudaGetLastError());
@@ -493,7 +498,7 @@ static int launch_conv_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const C
   const int grid = tiles < g_num_sms ? tiles : g_num_sms;
   {
     ProfileScope ps(name, stream, flops);
-    k_conv_umma<BN><<<grid, kConvThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, p);
+    k_conv_umma<BN><<<grid, conv_threads(BN), Cfg::kSmemBytes, stream>>>(tmA, tmB, p);
   }
   count_launch(1);
   HIPAC_CHECK_CUDA(cudaGetLastError());
