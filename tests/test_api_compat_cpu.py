@@ -101,3 +101,19 @@ def test_cli_rejects_unknown_flags_and_gates_on_data(tmp_path, monkeypatch, caps
     cli.main(["--extract_features"])
     assert "Patches must be extracted at level 3 before extracting features." in capsys.readouterr().out
     assert not cli.features_extracted(3)
+
+
+def test_heatmap_and_froc_csv(tmp_path):
+    import torch
+    from ss25_hierarchical_multiscale_image_classification_b200 import heatmap as hm
+    coords = torch.tensor([[0, 0], [448, 224], [224, 672]], dtype=torch.int32)
+    logits = torch.tensor([[2.0, 0.0], [0.0, 2.0], [0.0, 0.0]])
+    grid = hm.heatmap(coords, logits, width=1000, height=900, stride=224, fill=-1.0)
+    assert grid.shape == (5, 5)
+    p = torch.softmax(logits, 1)[:, 1]
+    assert torch.allclose(grid[0, 0], p[0]) and torch.allclose(grid[1, 2], p[1]) and torch.allclose(grid[3, 1], p[2])
+    assert int((grid == -1.0).sum()) == 22
+    n = hm.write_froc_csv(str(tmp_path / "t.csv"), coords, logits, level=2, patch=448, threshold=0.4)
+    rows = [l.split(",") for l in open(tmp_path / "t.csv").read().split()]
+    assert n == 2 and rows[0][1:] == [str((448 + 224) * 4), str((224 + 224) * 4)]   # level-0 coordinates of the centre
+    assert abs(float(rows[0][0]) - float(p[1])) < 1e-5
