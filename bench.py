@@ -46,28 +46,57 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    """SM clock / throttle reasons sampled DURING the timed region: NVML in-process every 10 ms
+    (nvidia-smi every 200 ms as the fallback)."""
 
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
-        self.index, self.rows, self._stop = index, [], threading.Event()
+        self.index, self.sm, self.flags, self.max_mhz, self._stop = index, [], set(), None, threading.Event()
+        self.source = "nvml"
         self._t = threading.Thread(target=self._run, daemon=True)
 
-    def _run(self):
+    def _run_nvml(self):
+        import pynvml as nv
+        nv.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = int(vis.split(",")[self.index]) if vis and all(v.strip().isdigit() for v in vis.split(",")) else self.index
+        h = nv.nvmlDeviceGetHandleByIndex(phys)
+        self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+        names = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown, "hw_thermal_slowdown": nv.nvmlClocksEventReasonHwThermalSlowdown,
+                 "sw_thermal_slowdown": nv.nvmlClocksEventReasonSwThermalSlowdown, "sw_power_cap": nv.nvmlClocksEventReasonSwPowerCap}
+        while not self._stop.is_set():
+            self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+            r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+            self.flags.update(n for n, bit in names.items() if r & bit)
+            self._stop.wait(0.01)
+
+    def _run_smi(self):
+        self.source = "nvidia-smi"
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         while not self._stop.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
                                       str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
                 if out:
-                    self.rows.append([c.strip() for c in out.split(",")])
+                    c = [v.strip() for v in out.split(",")]
+                    self.sm.append(float(c[0]))
+                    self.max_mhz = float(c[1])
+                    self.flags.update(n for i, n in enumerate(names) if c[2 + i].lower().startswith("active"))
             except Exception:
                 pass
             self._stop.wait(0.2)
 
+    def _run(self):
+        try:
+            self._run_nvml()
+        except Exception:
+            self._run_smi()
+
     def __enter__(self):
         self._t.start()
+        time.sleep(0.03)
         return self
 
     def __exit__(self, *a):
@@ -75,13 +104,10 @@ class ClockSampler:
         self._t.join(timeout=6)
 
     def summary(self):
-        if not self.rows:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
-        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows)]
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
-                "samples": len(self.rows)}
+        if not self.sm:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"]}
+        return {"sm_mhz": statistics.median(self.sm), "sm_min_mhz": min(self.sm), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.flags), "samples": len(self.sm), "source": self.source}
 
 
 def shard_rows(ny_total: int, world: int, rank: int):

@@ -117,6 +117,11 @@ int hipac_resnet18_conv_layer(const void* d_packed, int num_classes, int layer,
                               const void* d_in, const void* d_residual, void* d_out,
                               int n_patches, int relu, void* stream);
 
+/* Test hook: conv2 of layer{2,3,4}.0 with its 1x1/stride-2 projection shortcut fused into the same accumulator:
+ * out = relu(conv3x3(d_in) + bn + conv1x1_s2(d_block_in) + bn); stage 0/1/2 = layer2/3/4. */
+int hipac_resnet18_conv_ds_fused(const void* d_packed, int num_classes, int stage, const void* d_in, const void* d_block_in,
+                                 void* d_out, int n_patches, void* stream);
+
 /* Test hook: the fused stem (conv1 + folded BN + ReLU + 3x3/s2 max pool): S2D16 batch -> bf16 [n][56][56][64]. */
 int hipac_resnet18_stem(const void* d_packed, int num_classes, const void* d_in, void* d_out, int n_patches, void* stream);
 

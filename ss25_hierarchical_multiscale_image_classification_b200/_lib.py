@@ -98,6 +98,8 @@ def _declare(l):
     l.hipac_resnet18_workspace_bytes.argtypes = [i32, i32]
     l.hipac_resnet18_forward.restype = i32
     l.hipac_resnet18_forward.argtypes = [vp, i32, vp, i32, i32, vp, vp, vp, sz, i32, vp]
+    l.hipac_resnet18_conv_ds_fused.restype = i32
+    l.hipac_resnet18_conv_ds_fused.argtypes = [vp, i32, i32, vp, vp, vp, i32, vp]
     l.hipac_resnet18_stem.restype = i32
     l.hipac_resnet18_stem.argtypes = [vp, i32, vp, vp, i32, vp]
     l.hipac_debug_umma_shift.restype = i32
@@ -114,7 +116,7 @@ EXPORTS = [
     "hipac_last_error", "hipac_abi_version", "hipac_launch_count", "hipac_tile_scan_workspace_bytes",
     "hipac_tile_scan", "hipac_pillow_coeffs", "hipac_normalize_lut_bf16", "hipac_resnet18_packed_bytes",
     "hipac_resnet18_pack", "hipac_resnet18_workspace_bytes", "hipac_resnet18_forward",
-    "hipac_resnet18_conv_layer", "hipac_profile_enable", "hipac_profile_report", "hipac_debug_umma_shift", "hipac_resnet18_stem",
+    "hipac_resnet18_conv_layer", "hipac_profile_enable", "hipac_profile_report", "hipac_debug_umma_shift", "hipac_resnet18_stem", "hipac_resnet18_conv_ds_fused",
 ]
 
 

@@ -27,7 +27,9 @@ struct ConvParams {
   int stride, pad_w, pad_h;
   int kw;            // filter width (taps per filter row)
   int kc_blocks;     // 64-channel blocks per tap (cin / 64)
-  int num_kb;        // k-blocks per tile
+  int num_kb;        // k-blocks per tile from the main operand
+  int num_kb2;       // extra k-blocks from the second operand (fused 1x1 projection shortcut), 0 if none
+  int stride2;       // traversal stride of the second operand (pad 0, 1x1)
   int num_m_tiles, num_n_tiles;
   int cout;
   int relu;
@@ -119,7 +121,8 @@ struct ConvCfg {
 
 template <int BN>
 __global__ void __launch_bounds__(conv_threads(BN), 1)
-k_conv_umma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvParams p) {
+k_conv_umma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+            const __grid_constant__ CUtensorMap tmA2, const ConvParams p) {
   using Cfg = ConvCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -133,6 +136,7 @@ k_conv_umma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   if (threadIdx.x == 0) {
     ptx::prefetch_tensormap(&tmA);
     ptx::prefetch_tensormap(&tmB);
+    if (p.num_kb2) ptx::prefetch_tensormap(&tmA2);
     for (int s = 0; s < Cfg::kStages; s++) ptx::mbar_init(&full[s], 1), ptx::mbar_init(&empty[s], 1);
     for (int a = 0; a < 2; a++) ptx::mbar_init(&tfull[a], 1), ptx::mbar_init(&tempty[a], 4);
     ptx::fence_barrier_init();
@@ -160,7 +164,7 @@ k_conv_umma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const int img = m0 / p.hw_out, rem = m0 - img * p.hw_out;
         const int p0 = rem / p.wout, q0 = rem - p0 * p.wout;
         const int cw = q0 * p.stride - p.pad_w, ch = p0 * p.stride - p.pad_h;
-        for (int kb = 0; kb < p.num_kb; kb++) {
+        for (int kb = 0; kb < p.num_kb + p.num_kb2; kb++) {
           ptx::mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* a_dst = base + stage * Cfg::kStage;
           uint8_t* b_dst = a_dst + kABytes;
@@ -168,7 +172,10 @@ k_conv_umma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           const int r = tap / p.kw, s = tap - r * p.kw;
           if (ptx::elect_one()) {
             ptx::mbar_arrive_expect_tx(&full[stage], Cfg::kStage);
-            ptx::tma_load_im2col_4d(a_dst, &tmA, &full[stage], kc * 64, cw, ch, img, (uint16_t)s, (uint16_t)r);
+            if (kb < p.num_kb)
+              ptx::tma_load_im2col_4d(a_dst, &tmA, &full[stage], kc * 64, cw, ch, img, (uint16_t)s, (uint16_t)r);
+            else  // fused projection shortcut: 1x1 / stride2 / pad 0 over the block input, channels (kb - num_kb) * 64
+              ptx::tma_load_im2col_4d(a_dst, &tmA2, &full[stage], (kb - p.num_kb) * 64, q0 * p.stride2, p0 * p.stride2, img, 0, 0);
             ptx::tma_load_2d(b_dst, &tmB, &full[stage], kb * 64, n_tile * BN);
           }
           __syncwarp();
@@ -187,7 +194,7 @@ k_conv_umma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         ptx::mbar_wait(&tempty[acc], acc_phase ^ 1);  // epilogue has drained this accumulator
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kb = 0; kb < p.num_kb; kb++) {
+        for (int kb = 0; kb < p.num_kb + p.num_kb2; kb++) {
           ptx::mbar_wait(&full[stage], phase);
           ptx::tc_fence_after();
           const uint32_t a_addr = ptx::smem_u32(base + stage * Cfg::kStage);
@@ -340,6 +347,7 @@ static EncodeIm2colFn g_encode_im2col = nullptr;
 static EncodeTiledFn g_encode_tiled = nullptr;
 static int g_num_sms = 0;
 static bool g_use_fused_stem = true;   // HIPAC_FUSED_STEM=0 runs conv1 and the max pool as two kernels
+static bool g_fuse_downsample = true; // HIPAC_FUSE_DS=0 runs the 1x1 projection shortcuts as separate kernels
 static bool g_use_row_kernels = true;  // HIPAC_CONV_ROWS=0 forces the im2col kernel everywhere (A/B comparison)
 
 static int init_driver_api() {
@@ -357,6 +365,7 @@ static int init_driver_api() {
   HIPAC_CHECK_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
   if (const char* e = getenv("HIPAC_CONV_ROWS")) g_use_row_kernels = atoi(e) != 0;
   if (const char* e = getenv("HIPAC_FUSED_STEM")) g_use_fused_stem = atoi(e) != 0;
+  if (const char* e = getenv("HIPAC_FUSE_DS")) g_fuse_downsample = atoi(e) != 0;
   return 0;
 }
 
@@ -487,7 +496,7 @@ static int run_stem(const uint8_t* d_packed, const PackedLayout& L, const void* 
 
 template <int BN>
 static int launch_conv_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvParams& p, cudaStream_t stream,
-                         const char* name, double flops) {
+                         const char* name, double flops, const CUtensorMap* tmA2 = nullptr) {
   using Cfg = ConvCfg<BN>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -498,7 +507,7 @@ static int launch_conv_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const C
   const int grid = tiles < g_num_sms ? tiles : g_num_sms;
   {
     ProfileScope ps(name, stream, flops);
-    k_conv_umma<BN><<<grid, conv_threads(BN), Cfg::kSmemBytes, stream>>>(tmA, tmB, p);
+    k_conv_umma<BN><<<grid, conv_threads(BN), Cfg::kSmemBytes, stream>>>(tmA, tmB, tmA2 ? *tmA2 : tmA, p);
   }
   count_launch(1);
   HIPAC_CHECK_CUDA(cudaGetLastError());
@@ -525,6 +534,7 @@ static int run_conv(const uint8_t* d_packed, const PackedLayout& L, int layer, c
   p.residual = reinterpret_cast<const __nv_bfloat16*>(residual);
   p.out = reinterpret_cast<__nv_bfloat16*>(out);
   p.num_m_tiles = (p.M_total + kBM - 1) / kBM;
+  p.num_kb2 = 0, p.stride2 = 1;
   const int bn = cs.cout >= 256 ? 256 : (cs.cout >= 128 ? 128 : 64);
   p.num_n_tiles = cs.cout / bn;
   CUtensorMap tmA, tmB;
@@ -550,6 +560,38 @@ static int run_conv(const uint8_t* d_packed, const PackedLayout& L, int layer, c
   const double flops = 2.0 * p.M_total * cs.cout * K;
   if (bn == 256) return launch_conv_t<256>(tmA, tmB, p, stream, name, flops);
   return bn == 128 ? launch_conv_t<128>(tmA, tmB, p, stream, name, flops) : launch_conv_t<64>(tmA, tmB, p, stream, name, flops);
+}
+
+// conv2 of a stage's first block with its projection shortcut fused: out = relu(conv3x3(in) + conv1x1_s2(block_in) + bias).
+// Both GEMMs accumulate into the same TMEM tile (the shortcut is extra K-blocks), so the shortcut tensor never exists.
+static int run_conv_ds_fused(const uint8_t* d_packed, const PackedLayout& L, int s, const void* in, const void* block_in, void* out,
+                             int n, cudaStream_t stream) {
+  const int lc = fused_conv_layer(s), ld = fused_ds_layer(s);
+  const ConvSpec &cs = kConvs[lc], &ds = kConvs[ld];
+  ConvParams p;
+  p.M_total = n * cs.hout * cs.hout;
+  p.hw_out = cs.hout * cs.hout, p.wout = cs.hout;
+  p.cout = cs.cout, p.relu = 1;
+  p.bias = reinterpret_cast<const float*>(d_packed + L.bf_off[s]);
+  p.residual = nullptr;
+  p.out = reinterpret_cast<__nv_bfloat16*>(out);
+  p.num_m_tiles = (p.M_total + kBM - 1) / kBM;
+  const int bn = cs.cout >= 256 ? 256 : 128;
+  p.num_n_tiles = cs.cout / bn;
+  p.stride = 1, p.pad_w = p.pad_h = 1, p.kw = 3, p.kc_blocks = cs.cin / 64, p.num_kb = 9 * p.kc_blocks;
+  p.num_kb2 = ds.cin / 64, p.stride2 = 2;
+  CUtensorMap tmA, tmA2, tmB;
+  if (int e = make_weight_map(&tmB, d_packed + L.wf_off[s], cs.cout, fused_gemm_k(s), bn)) return e;
+  Im2colDesc d{n, cs.hin, cs.hin, cs.cin, (int64_t)cs.cin * 2, (int64_t)cs.hin * cs.cin * 2, (int64_t)cs.hin * cs.hin * cs.cin * 2,
+               3, 3, 1, 1, 1, 1, 1};
+  if (int e = make_im2col_map(&tmA, in, d)) return e;
+  Im2colDesc d2{n, ds.hin, ds.hin, ds.cin, (int64_t)ds.cin * 2, (int64_t)ds.hin * ds.cin * 2, (int64_t)ds.hin * ds.hin * ds.cin * 2,
+                1, 1, 2, 0, 0, 0, 0};
+  if (int e = make_im2col_map(&tmA2, block_in, d2)) return e;
+  static const char* kNames[3] = {"conv3x3+ds_c128", "conv3x3+ds_c256", "conv3x3+ds_c512"};
+  const double flops = 2.0 * p.M_total * cs.cout * fused_gemm_k(s);
+  return bn == 256 ? launch_conv_t<256>(tmA, tmB, p, stream, kNames[s], flops, &tmA2)
+                   : launch_conv_t<128>(tmA, tmB, p, stream, kNames[s], flops, &tmA2);
 }
 
 static uint16_t host_bf16(float f) {
@@ -614,6 +656,20 @@ extern "C" int hipac_resnet18_pack(const float* const* t, int num_tensors, int n
           }
     }
   }
+  for (int s = 0; s < 3; s++) {
+    const int lc = fused_conv_layer(s), ld = fused_ds_layer(s);
+    const int cout = kConvs[lc].cout, k1 = conv_gemm_k(lc), k2 = conv_gemm_k(ld), kf = k1 + k2;
+    const uint16_t* w1 = reinterpret_cast<const uint16_t*>(dst + L.w_off[lc]);
+    const uint16_t* w2 = reinterpret_cast<const uint16_t*>(dst + L.w_off[ld]);
+    const float *b1 = reinterpret_cast<const float*>(dst + L.b_off[lc]), *b2 = reinterpret_cast<const float*>(dst + L.b_off[ld]);
+    uint16_t* wf = reinterpret_cast<uint16_t*>(dst + L.wf_off[s]);
+    float* bf = reinterpret_cast<float*>(dst + L.bf_off[s]);
+    for (int o = 0; o < cout; o++) {
+      memcpy(wf + (size_t)o * kf, w1 + (size_t)o * k1, (size_t)k1 * 2);
+      memcpy(wf + (size_t)o * kf + k1, w2 + (size_t)o * k2, (size_t)k2 * 2);
+      bf[o] = b1[o] + b2[o];
+    }
+  }
   if (num_classes > 0) {
     const float *fw = t[100], *fb = t[101];
     HIPAC_REQUIRE(fw && fb, "num_classes > 0 needs fc weight and bias");
@@ -638,6 +694,16 @@ extern "C" int hipac_resnet18_conv_layer(const void* d_packed, int num_classes, 
   const PackedLayout L = packed_layout(num_classes);
   return run_conv(reinterpret_cast<const uint8_t*>(d_packed), L, layer, d_in, d_residual, d_out, n_patches, relu != 0,
                   (cudaStream_t)stream_);
+}
+
+extern "C" int hipac_resnet18_conv_ds_fused(const void* d_packed, int num_classes, int stage, const void* d_in, const void* d_block_in,
+                                            void* d_out, int n_patches, void* stream_) {
+  HIPAC_REQUIRE(d_packed && d_in && d_block_in && d_out && n_patches > 0, "bad arguments");
+  HIPAC_REQUIRE(stage >= 0 && stage < 3, "stage must be 0 (layer2), 1 (layer3) or 2 (layer4)");
+  if (int e = init_driver_api()) return e;
+  const PackedLayout L = packed_layout(num_classes);
+  return run_conv_ds_fused(reinterpret_cast<const uint8_t*>(d_packed), L, stage, d_in, d_block_in, d_out, n_patches,
+                           (cudaStream_t)stream_);
 }
 
 extern "C" int hipac_resnet18_stem(const void* d_packed, int num_classes, const void* d_in, void* d_out, int n_patches,
@@ -711,8 +777,12 @@ extern "C" int hipac_resnet18_forward(const void* d_packed, int num_classes, con
     for (int s = 0; s < 3; s++) {
       const int l0 = 5 + 5 * s;
       if ((e = conv(l0, A, nullptr, B, true))) return e;           // 3x3 / stride 2
-      if ((e = conv(l0 + 2, A, nullptr, D, false))) return e;      // downsample 1x1 / stride 2 (+BN), no ReLU
-      if ((e = conv(l0 + 1, B, D, C, true))) return e;             // 3x3 + shortcut + ReLU
+      if (g_fuse_downsample) {
+        if ((e = run_conv_ds_fused(pk, L, s, B, A, C, n, stream))) return e;   // 3x3 + 1x1/s2 projection + ReLU, one accumulator
+      } else {
+        if ((e = conv(l0 + 2, A, nullptr, D, false))) return e;    // downsample 1x1 / stride 2 (+BN), no ReLU
+        if ((e = conv(l0 + 1, B, D, C, true))) return e;           // 3x3 + shortcut + ReLU
+      }
       if ((e = conv(l0 + 3, C, nullptr, B, true)) || (e = conv(l0 + 4, B, C, A, true))) return e;
     }
     ProfileScope ps_pool("avgpool_fc", stream, (double)n * (49 * 512 * 2 + 512 * 4));

@@ -32,8 +32,15 @@ struct PackedLayout {
   size_t w_off[HIPAC_RESNET18_NUM_CONVS];  // bf16 [cout][K]
   size_t b_off[HIPAC_RESNET18_NUM_CONVS];  // f32 [cout]
   size_t fc_w_off, fc_b_off;               // f32 [k][512], f32 [k]
+  // projection-shortcut fusion: for stage s (layer2..4) conv2 of block 0 and its 1x1/stride-2 downsample share one
+  // accumulator: weights [cout][9*cout + cin_ds] = conv2's K followed by the downsample's K, bias = sum of both
+  size_t wf_off[3], bf_off[3];
   size_t total;
 };
+
+static inline int fused_conv_layer(int s) { return 6 + 5 * s; }   // layerL.0.conv2
+static inline int fused_ds_layer(int s) { return 7 + 5 * s; }     // layerL.0.downsample.0
+static inline int fused_gemm_k(int s) { return conv_gemm_k(fused_conv_layer(s)) + conv_gemm_k(fused_ds_layer(s)); }
 
 static inline PackedLayout packed_layout(int num_classes) {
   PackedLayout L;
@@ -49,6 +56,10 @@ static inline PackedLayout packed_layout(int num_classes) {
   }
   L.fc_w_off = bump((size_t)(num_classes > 0 ? num_classes : 0) * 512 * 4);
   L.fc_b_off = bump((size_t)(num_classes > 0 ? num_classes : 0) * 4);
+  for (int s = 0; s < 3; s++) {
+    L.wf_off[s] = bump((size_t)kConvs[fused_conv_layer(s)].cout * fused_gemm_k(s) * 2);
+    L.bf_off[s] = bump((size_t)kConvs[fused_conv_layer(s)].cout * 4);
+  }
   L.total = off;
   return L;
 }

@@ -131,3 +131,15 @@ def stem(packed: PackedResNet18, x: torch.Tensor) -> torch.Tensor:
                                torch.cuda.current_stream(x.device).cuda_stream)
     _lib.check(rc, "hipac_resnet18_stem")
     return out
+
+
+def conv_ds_fused(packed: PackedResNet18, stage: int, x: torch.Tensor, block_in: torch.Tensor) -> torch.Tensor:
+    """Test hook: conv2 of layer{2,3,4}.0 + fused 1x1/s2 projection shortcut + ReLU (stage 0/1/2)."""
+    l = _lib.lib()
+    n, cout, hout = int(x.shape[0]), (128, 256, 512)[stage], (28, 14, 7)[stage]
+    out = torch.empty((n, hout, hout, cout), dtype=torch.bfloat16, device=x.device)
+    rc = l.hipac_resnet18_conv_ds_fused(packed.blob.data_ptr(), packed.num_classes, stage, x.contiguous().data_ptr(),
+                                        block_in.contiguous().data_ptr(), out.data_ptr(), n,
+                                        torch.cuda.current_stream(x.device).cuda_stream)
+    _lib.check(rc, "hipac_resnet18_conv_ds_fused")
+    return out

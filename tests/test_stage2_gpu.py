@@ -151,3 +151,28 @@ def test_fused_stem_vs_torch_fp32(net_and_packed, n):
     scale = float(ref.abs().max())
     err = float((got - ref).abs().max())
     assert err <= 1.5 * 2.0 ** -8 * scale + 1e-3, f"stem: max err {err} at scale {scale}"
+
+
+@pytest.mark.parametrize("n", [1, 5])
+@pytest.mark.parametrize("stage", [0, 1, 2])
+def test_fused_projection_shortcut_vs_torch_fp32(net_and_packed, stage, n):
+    """relu(conv3x3(x) + conv1x1_s2(block_in) + both folded BN biases) accumulated in one TMEM tile."""
+    from ss25_hierarchical_multiscale_image_classification_b200 import features
+    net, packed = net_and_packed
+    lc, ld = 6 + 5 * stage, 7 + 5 * stage
+    cin, cout, _, _, _, hin = SPECS[lc]
+    dcin, _, _, _, _, dhin = SPECS[ld]
+    g = torch.Generator(device="cuda").manual_seed(50 + stage)
+    x = torch.randn((n, hin, hin, cin), generator=g, device="cuda").bfloat16()
+    xb = torch.randn((n, dhin, dhin, dcin), generator=g, device="cuda").bfloat16()
+    w1, b1 = _folded(net, lc)
+    w2, b2 = _folded(net, ld)
+    ref = torch.nn.functional.conv2d(x.float().permute(0, 3, 1, 2), w1, b1, stride=1, padding=1) + \
+        torch.nn.functional.conv2d(xb.float().permute(0, 3, 1, 2), w2, b2, stride=2, padding=0)
+    ref = torch.relu(ref)
+    out = features.conv_ds_fused(packed, stage, x, xb)
+    torch.cuda.synchronize()
+    got = out.float().permute(0, 3, 1, 2)
+    scale = float(ref.abs().max())
+    err = float((got - ref).abs().max())
+    assert err <= 1.5 * 2.0 ** -8 * scale + 1e-3, f"stage {stage}: max err {err} at scale {scale}"
