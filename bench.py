@@ -144,8 +144,8 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     import __graft_entry__ as ge
-    from oracle import hipac_oracle as orc   # weights recipe only (seeded torchvision resnet18)
     from ss25_hierarchical_multiscale_image_classification_b200 import _lib, features, pipeline, sharding
+    from ss25_hierarchical_multiscale_image_classification_b200.synthetic import seeded_resnet18
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -157,7 +157,7 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     ge.build()
-    net = orc.make_resnet18(seed=0, classifier=True)                      # random-init weights (BASELINE config)
+    net = seeded_resnet18(seed=0, classifier=True)                        # random-init weights (BASELINE config)
     packed = features.pack_resnet18(net.state_dict(), dev)
     img_h, msk_h, (i0, i1, y0, H) = build_slab(world, rank)
     img_d, msk_d = img_h.to(dev), msk_h.to(dev)

@@ -225,26 +225,10 @@ def extract_patches_oracle(level_img: np.ndarray, mask: np.ndarray | None, level
 # stage 2: torch fp32 ResNet18 (src/models/resnet.py:22-77)
 # --------------------------------------------------------------------------
 def make_resnet18(seed: int = 0, classifier: bool = True):
-    """Seeded random-init torchvision resnet18 (+ Linear(512,2) head), eval mode.
-
-    BatchNorm running stats are perturbed away from (0,1) so BN folding is
-    actually exercised by the parity tests."""
-    import torch
-    import torchvision
-
-    g = torch.Generator().manual_seed(seed)
-    torch.manual_seed(seed)
-    net = torchvision.models.resnet18(weights=None)
-    if classifier:
-        net.fc = torch.nn.Linear(512, 2)
-    with torch.no_grad():
-        for m in net.modules():
-            if isinstance(m, torch.nn.BatchNorm2d):
-                m.running_mean.copy_(0.1 * torch.randn(m.num_features, generator=g))
-                m.running_var.copy_(0.75 + 0.5 * torch.rand(m.num_features, generator=g))
-                m.weight.copy_(0.8 + 0.4 * torch.rand(m.num_features, generator=g))
-                m.bias.copy_(0.1 * torch.randn(m.num_features, generator=g))
-    return net.eval()
+    """Seeded random-init torchvision resnet18 (+ Linear(512,2) head), eval mode: the shared synthetic-weights
+    recipe (``synthetic.seeded_resnet18``), so both sides of every parity test load the same state dict."""
+    from ss25_hierarchical_multiscale_image_classification_b200.synthetic import seeded_resnet18
+    return seeded_resnet18(seed, classifier)
 
 
 def resnet18_features_fp32(net, images_u8: np.ndarray, batch: int = 64):

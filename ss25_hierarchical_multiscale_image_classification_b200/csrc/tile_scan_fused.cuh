@@ -99,9 +99,43 @@ __global__ void __launch_bounds__(256) k_cell_stats(ScanParams p, FusedGeom G) {
   const int xb = cx * G.g, xe = min(p.W, xb + G.g);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint32_t s = 0, any = 0;
-  for (int r = r0 + warp; r < r1; r += 8) {
-    s += warp_bytes_sum(p.rgb, (int64_t)r * p.pitch + (int64_t)xb * 3, (xe - xb) * 3, 0, lane);
-    if (p.mask) any |= warp_bytes_any(p.mask, (int64_t)r * p.mask_pitch + xb, xe - xb, lane);
+  const int nbytes = (xe - xb) * 3;
+  if ((p.pitch & 15) == 0 && ((reinterpret_cast<uintptr_t>(p.rgb) + (size_t)xb * 3) & 15) == 0) {
+    // fast path: every row of the band starts 16-byte aligned -> flatten (row, chunk) over the CTA and keep
+    // several independent 128-bit loads in flight per thread
+    const int nfull = nbytes >> 4, nrows = r1 - r0, total = nrows * nfull;
+    const uint8_t* base = p.rgb + (int64_t)r0 * p.pitch + (int64_t)xb * 3;
+    for (int i0 = threadIdx.x; i0 < total; i0 += 256 * 4) {
+      uint4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int idx = i0 + u * 256;
+        const int rr = idx / nfull, k = idx - rr * nfull;
+        v[u] = idx < total ? ldg_nc_v4(base + (int64_t)rr * p.pitch + k * 16) : make_uint4(0, 0, 0, 0);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; u++) s += bytesum4(v[u].x) + bytesum4(v[u].y) + bytesum4(v[u].z) + bytesum4(v[u].w);
+    }
+    const int tail = nbytes & 15;   // right image edge only
+    if (tail)
+      for (int idx = threadIdx.x; idx < nrows * tail; idx += 256) s += base[(int64_t)(idx / tail) * p.pitch + nfull * 16 + idx % tail];
+  } else {
+    for (int r = r0 + warp; r < r1; r += 8)
+      s += warp_bytes_sum(p.rgb, (int64_t)r * p.pitch + (int64_t)xb * 3, nbytes, 0, lane);
+  }
+  if (p.mask) {
+    const int mbytes = xe - xb;
+    if ((p.mask_pitch & 15) == 0 && ((reinterpret_cast<uintptr_t>(p.mask) + (size_t)xb) & 15) == 0 && (mbytes & 15) == 0) {
+      const int nfull = mbytes >> 4, total = (r1 - r0) * nfull;
+      const uint8_t* base = p.mask + (int64_t)r0 * p.mask_pitch + xb;
+      for (int idx = threadIdx.x; idx < total; idx += 256) {
+        const int rr = idx / nfull, k = idx - rr * nfull;
+        const uint4 v = ldg_nc_v4(base + (int64_t)rr * p.mask_pitch + k * 16);
+        any |= v.x | v.y | v.z | v.w;
+      }
+    } else {
+      for (int r = r0 + warp; r < r1; r += 8) any |= warp_bytes_any(p.mask, (int64_t)r * p.mask_pitch + xb, mbytes, lane);
+    }
   }
   for (int o = 16; o; o >>= 1) {
     s += __shfl_xor_sync(0xffffffffu, s, o);
@@ -194,6 +228,7 @@ __global__ void __launch_bounds__(256) k_downsample_planes(ScanParams p, FusedGe
   }
   __syncthreads();
   const int ncols = s_ncols;
+  const int n_int = Ib1 - I0;                              // interior columns come first in the work-column table
   const int nitems = ncols * 3;
 
   // ---- image window of this CTA ----
@@ -289,57 +324,64 @@ __global__ void __launch_bounds__(256) k_downsample_planes(ScanParams p, FusedGe
       const uint8_t* rowp = stage + warp * ROWCAP;
       const int phase = (r < 0 || r >= Himg) ? 0 : ((r * pm + pc) & 15);
       uint8_t* hrow = hbuf + warp * HB;
-      for (int col = lane; col < ncols; col += 32) {
+      // interior columns col < n_int are I = I0 + col: window start advances by 3F bytes per column
+      const int A0 = kPlaneFront + phase + (F * I0 - HALF - px0c) * 3;     // >= 4: the front pad absorbs I == 0
+      for (int col = lane; col < n_int; col += 32) {
+        uint8_t* hout = hrow + col * 3;
+        // 2F taps x 3 interleaved channels = 6F bytes: word loads, funnel-shift to the window start, PRMT the
+        // stride-3 bytes of each channel into one register, dp4a with the (2m+1) weights (exact: the weights are
+        // (2m+1)/2^SHIFT, so Pillow's 22-bit fixed point reduces to (T + 2^(SHIFT-1)) >> SHIFT)
+        const int A = A0 + 3 * F * col;
+        const uint32_t* wp = reinterpret_cast<const uint32_t*>(rowp) + (A >> 2);
+        const uint32_t sh = (A & 3) * 8;
+        constexpr int NW = 6 * F / 4;
+        uint32_t wd[NW + 1];
+#pragma unroll
+        for (int k = 0; k <= NW; k++) wd[k] = wp[k];
+#pragma unroll
+        for (int k = 0; k < NW; k++) wd[k] = __funnelshift_r(wd[k], wd[k + 1], sh);
+        uint32_t T0 = 0, T1 = 0, T2 = 0;
+#pragma unroll
+        for (int q = 0; q < NI / 4; q++) {
+          uint32_t wt = 0;
+#pragma unroll
+          for (int jj = 0; jj < 4; jj++) {
+            const int t = 4 * q + jj;
+            wt |= (uint32_t)(t < F ? 2 * t + 1 : 2 * (NI - 1 - t) + 1) << (8 * jj);
+          }
+          const uint32_t a = wd[3 * q], b = wd[3 * q + 1], cc = wd[3 * q + 2];
+          T0 = __dp4a(__byte_perm(__byte_perm(a, b, 0x0630), cc, 0x5210), wt, T0);
+          T1 = __dp4a(__byte_perm(__byte_perm(a, b, 0x0741), cc, 0x6210), wt, T1);
+          T2 = __dp4a(__byte_perm(__byte_perm(a, b, 0x0052), cc, 0x7410), wt, T2);
+        }
+        hout[0] = (uint8_t)((T0 + (1u << (SHIFT - 1))) >> SHIFT);
+        hout[1] = (uint8_t)((T1 + (1u << (SHIFT - 1))) >> SHIFT);
+        hout[2] = (uint8_t)((T2 + (1u << (SHIFT - 1))) >> SHIFT);
+      }
+      // ring-variant columns (clamped 3F/2-tap windows, 22-bit weights): a handful per band
+      for (int col = n_int + lane; col < ncols; col += 32) {
         const int I = col_I[col], kind = col_kind[col];
         uint8_t* hout = hrow + col * 3;
-        if (kind == 0) {
-          // 2F taps x 3 interleaved channels = 6F bytes: word loads, funnel-shift to the window start, PRMT the
-          // stride-3 bytes of each channel into one register, dp4a with the (2m+1) weights (exact: the weights are
-          // (2m+1)/2^SHIFT, so Pillow's 22-bit fixed point reduces to (T + 2^(SHIFT-1)) >> SHIFT)
-          const int A = kPlaneFront + phase + (F * I - HALF - px0c) * 3;   // >= 4: the front pad absorbs I == 0
-          const uint32_t* wp = reinterpret_cast<const uint32_t*>(rowp) + (A >> 2);
-          const uint32_t sh = (A & 3) * 8;
-          constexpr int NW = 6 * F / 4;
-          uint32_t wd[NW + 1];
+        const uint8_t* pix = rowp + kPlaneFront + phase + (kind == 1 ? F * I - px0c : F * I - HALF - px0c) * 3;
+        const int32_t* kh = kind == 1 ? cs.left : cs.right;
+        int a0 = 1 << (kPrecisionBits - 1), a1 = a0, a2 = a0;
 #pragma unroll
-          for (int k = 0; k <= NW; k++) wd[k] = wp[k];
-#pragma unroll
-          for (int k = 0; k < NW; k++) wd[k] = __funnelshift_r(wd[k], wd[k + 1], sh);
-          uint32_t T0 = 0, T1 = 0, T2 = 0;
-#pragma unroll
-          for (int q = 0; q < NI / 4; q++) {
-            uint32_t wt = 0;
-#pragma unroll
-            for (int jj = 0; jj < 4; jj++) {
-              const int t = 4 * q + jj;
-              wt |= (uint32_t)(t < F ? 2 * t + 1 : 2 * (NI - 1 - t) + 1) << (8 * jj);
-            }
-            const uint32_t a = wd[3 * q], b = wd[3 * q + 1], cc = wd[3 * q + 2];
-            T0 = __dp4a(__byte_perm(__byte_perm(a, b, 0x0630), cc, 0x5210), wt, T0);
-            T1 = __dp4a(__byte_perm(__byte_perm(a, b, 0x0741), cc, 0x6210), wt, T1);
-            T2 = __dp4a(__byte_perm(__byte_perm(a, b, 0x0052), cc, 0x7410), wt, T2);
-          }
-          hout[0] = (uint8_t)((T0 + (1u << (SHIFT - 1))) >> SHIFT);
-          hout[1] = (uint8_t)((T1 + (1u << (SHIFT - 1))) >> SHIFT);
-          hout[2] = (uint8_t)((T2 + (1u << (SHIFT - 1))) >> SHIFT);
-        } else {
-          const uint8_t* pix = rowp + kPlaneFront + phase + (kind == 1 ? F * I - px0c : F * I - HALF - px0c) * 3;
-          const int32_t* kh = kind == 1 ? cs.left : cs.right;
-          int a0 = 1 << (kPrecisionBits - 1), a1 = a0, a2 = a0;
-#pragma unroll
-          for (int t = 0; t < NE; t++) {
-            a0 += kh[t] * (int)pix[3 * t], a1 += kh[t] * (int)pix[3 * t + 1], a2 += kh[t] * (int)pix[3 * t + 2];
-          }
-          hout[0] = (uint8_t)min(max(a0 >> kPrecisionBits, 0), 255);
-          hout[1] = (uint8_t)min(max(a1 >> kPrecisionBits, 0), 255);
-          hout[2] = (uint8_t)min(max(a2 >> kPrecisionBits, 0), 255);
+        for (int t = 0; t < NE; t++) {
+          a0 += kh[t] * (int)pix[3 * t], a1 += kh[t] * (int)pix[3 * t + 1], a2 += kh[t] * (int)pix[3 * t + 2];
         }
+        hout[0] = (uint8_t)min(max(a0 >> kPrecisionBits, 0), 255);
+        hout[1] = (uint8_t)min(max(a1 >> kPrecisionBits, 0), 255);
+        hout[2] = (uint8_t)min(max(a2 >> kPrecisionBits, 0), 255);
       }
     }
     __syncthreads();
     // ---- vertical pass.  Stage row rr is image row r_stage + rr with (r + HALF) = F * (Ja0 + (8*st + rr) / F) + rr % F,
     //      so the tap index tb = rr % F is a compile-time constant of the unrolled loop. ----
     const int Jstage = Ja0 + (kPlaneG / F) * st;   // D row whose window starts at stage row 0
+    // ring-variant accumulators only matter for D rows on the patch-edge lattice (k*Sf and k*Sf + 223); the rows this
+    // stage feeds are Jstage-1 .. Jstage + 8/F - 1 (CTA-uniform test)
+    bool var = false;
+    for (int J = Jstage - 1; J < Jstage + kPlaneG / F; J++) var |= (J >= 0 && J % Sf == 0) || (J >= OUT - 1 && (J - (OUT - 1)) % Sf == 0);
 #pragma unroll
     for (int q = 0; q < IPT; q++) {
       if (it_off[q] < 0) continue;
@@ -353,10 +395,12 @@ __global__ void __launch_bounds__(256) k_downsample_planes(ScanParams p, FusedGe
         const int h = hp[rr * HB];
         B_int[q] += (2 * tb + 1) * h;
         A_int[q] += (2 * (F - 1 - tb) + 1) * h;
-        B_bot[q] += cs.right[tb] * h;
-        if (tb < HALF) A_bot[q] += cs.right[tb + F] * h;
-        if (tb >= HALF) B_top[q] += cs.left[tb - HALF] * h;
-        A_top[q] += cs.left[tb + HALF] * h;
+        if (var) {
+          B_bot[q] += cs.right[tb] * h;
+          if (tb < HALF) A_bot[q] += cs.right[tb + F] * h;
+          if (tb >= HALF) B_top[q] += cs.left[tb - HALF] * h;
+          A_top[q] += cs.left[tb + HALF] * h;
+        }
         if (tb == F - 1) {
           const int J = Jstage + rr / F - 1;       // the D row that just received its last tap
           if (J >= Ja0 && J < Ja1) {

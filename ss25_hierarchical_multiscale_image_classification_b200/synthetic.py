@@ -17,7 +17,7 @@ from __future__ import annotations
 
 import numpy as np
 
-__all__ = ["hash32", "SyntheticSlide", "make_level", "make_lesion_mask"]
+__all__ = ["hash32", "SyntheticSlide", "make_level", "make_lesion_mask", "seeded_resnet18"]
 
 _M32 = np.uint32(0xFFFFFFFF)
 
@@ -166,3 +166,28 @@ class SyntheticSlide:
 
     def close(self):
         pass
+
+
+def seeded_resnet18(seed: int = 0, classifier: bool = True):
+    """Seeded random-init torchvision resnet18 (+ ``Linear(512,2)`` head), eval mode -- the "random-init ResNet18"
+    of BASELINE.json's configs (the reference's trained checkpoint is not in its checkout, and its
+    ``--extract_features`` runs on random-init weights anyway).
+
+    BatchNorm statistics and affine parameters are perturbed away from (0, 1, 1, 0) so that BN folding is
+    actually exercised."""
+    import torch
+    import torchvision
+
+    g = torch.Generator().manual_seed(seed)
+    torch.manual_seed(seed)
+    net = torchvision.models.resnet18(weights=None)
+    if classifier:
+        net.fc = torch.nn.Linear(512, 2)
+    with torch.no_grad():
+        for m in net.modules():
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.running_mean.copy_(0.1 * torch.randn(m.num_features, generator=g))
+                m.running_var.copy_(0.75 + 0.5 * torch.rand(m.num_features, generator=g))
+                m.weight.copy_(0.8 + 0.4 * torch.rand(m.num_features, generator=g))
+                m.bias.copy_(0.1 * torch.randn(m.num_features, generator=g))
+    return net.eval()
