@@ -38,6 +38,14 @@ FLOP_PER_PATCH = 3.627e9          # SURVEY.md section 2.2 (conv 2*MAC + fc)
 S2D_BYTES = 112 * 112 * 16 * 2
 
 
+def ncu_traffic():
+    """DRAM bytes per step from the committed ncu capture (profiles/r01_traffic.json), or {} if absent."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+    except Exception:
+        return {}
+
+
 def measured_peaks():
     try:
         return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))), "measured"
@@ -222,6 +230,7 @@ def run_ours(args):
     prof = _lib.profile_report()
     _lib.profile(False)
     peaks, peak_src = measured_peaks()
+    traffic = ncu_traffic()
     conv = {k: v for k, v in prof.items() if k.startswith("conv")}
     conv_ms = sum(v["ms"] for v in conv.values())
     conv_flops = sum(v["work"] for v in conv.values())
@@ -262,13 +271,16 @@ def run_ours(args):
         "clocks": clk.summary(),
         "roofline": {"bound": "tensor", "kernel": "k_conv_umma (all 20 conv layers)", "achieved": round(conv_tf, 1),
                      "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                     "frac": round(conv_tf / peaks["bf16_tflops_sustained"], 4), "traffic": None, "peak_source": peak_src,
+                     "frac": round(conv_tf / peaks["bf16_tflops_sustained"], 4),
+                     "traffic": traffic.get("conv_dram_bytes_per_step"), "traffic_unit": "DRAM bytes per step over the 17 conv launches (ncu)",
+                     "algorithmic_flops_per_step": conv_flops / 2, "peak_source": peak_src,
                      "conv_ms_per_step": round(conv_ms / 2, 3)},
         "roofline_stage1": {"bound": "hbm", "kernel": "stage-1 tile scan (all kernels)",
                             "achieved": round(s1_bytes / (s1_ms * 1e-3) / 1e9, 1) if s1_ms else None,
                             "peak": peaks["hbm_gbs"], "unit": "GB/s",
                             "frac": round(s1_bytes / (s1_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], 4) if s1_ms else None,
-                            "ms_per_step": round(s1_ms, 3), "algorithmic_bytes": int(s1_bytes)},
+                            "ms_per_step": round(s1_ms, 3), "algorithmic_bytes": int(s1_bytes),
+                            "traffic": traffic.get("stage1_dram_bytes_per_step")},
         "kernels": kernels,
     }
     if cpu:
