@@ -126,7 +126,11 @@ def shard_rows(ny_total: int, world: int, rank: int):
 
 
 def build_slab(world: int, rank: int):
-    """Pinned host tensors of this rank's row slab (+ halo) of the N x 16384-row synthetic slide."""
+    """Pinned host tensors of this rank's row slab (+ halo) of the N x 16384-row synthetic slide.
+
+    The slide's content repeats every 16384 rows (row y shows row y mod 16384 of the N = 1 slide), so the per-GPU
+    work really is fixed as N grows: every rank tiles the same tissue layout; only the last rank sees the slide's
+    bottom edge (white-padded patches), exactly like the single rank at N = 1."""
     import torch
     from ss25_hierarchical_multiscale_image_classification_b200.synthetic import make_lesion_mask, make_level
     H = ROWS_PER_GPU * world
@@ -139,8 +143,12 @@ def build_slab(world: int, rank: int):
 
     def fill(r):
         r1 = min(r + 256, y1)
-        inp[r - y0:r1 - y0] = make_level(SEED, LEVEL, WIDTH, H, r, r1)
-        mnp[r - y0:r1 - y0] = make_lesion_mask(SEED, LEVEL, WIDTH, H, r, r1)
+        while r < r1:                                   # split at period boundaries
+            q = r % ROWS_PER_GPU
+            n = min(r1 - r, ROWS_PER_GPU - q)
+            inp[r - y0:r - y0 + n] = make_level(SEED, LEVEL, WIDTH, ROWS_PER_GPU, q, q + n)
+            mnp[r - y0:r - y0 + n] = make_lesion_mask(SEED, LEVEL, WIDTH, ROWS_PER_GPU, q, q + n)
+            r += n
 
     from concurrent.futures import ThreadPoolExecutor
     with ThreadPoolExecutor(max(1, min(16, (os.cpu_count() or 8) // max(1, world)))) as ex:
@@ -261,7 +269,8 @@ def run_ours(args):
                    "level": LEVEL, "patch": PATCH, "stride": STRIDE, "width": WIDTH, "rows_per_gpu": ROWS_PER_GPU,
                    "candidates_per_step": n_cand * world if world == 1 else None, "survivors_per_step": total_surv,
                    "candidates_per_s": round(n_cand * world / (ms_step * 1e-3), 1),
-                   "sharding": f"tile-row ranges over {world} rank(s); NCCL all-gather of counts/coords/labels/features",
+                   "sharding": f"tile-row ranges over {world} rank(s) of one {ROWS_PER_GPU * world}-row slide (content periodic in y, period "
+                               f"{ROWS_PER_GPU}); NCCL all-gather of counts/coords/labels/features/logits + canonical sort",
                    "cache": "inputs (0.8 GB image + 0.27 GB mask per GPU) exceed the 126 MB L2; no flush needed",
                    "resnet_chunk": args.chunk, "e2e_upload_groups": args.groups},
         "e2e": {"value": round(total_surv_e / (ms_e2e * 1e-3), 1), "unit": "patches/s",
