@@ -350,6 +350,16 @@ static bool g_use_fused_stem = true;   // HIPAC_FUSED_STEM=0 runs conv1 and the 
 static bool g_fuse_downsample = true; // HIPAC_FUSE_DS=0 runs the 1x1 projection shortcuts as separate kernels
 static bool g_use_row_kernels = true;  // HIPAC_CONV_ROWS=0 forces the im2col kernel everywhere (A/B comparison)
 
+// A/B switches for measurements; read once (the workspace size depends on them).
+static void read_env_flags() {
+  static bool done = false;
+  if (done) return;
+  done = true;
+  if (const char* e = getenv("HIPAC_CONV_ROWS")) g_use_row_kernels = atoi(e) != 0;
+  if (const char* e = getenv("HIPAC_FUSED_STEM")) g_use_fused_stem = atoi(e) != 0;
+  if (const char* e = getenv("HIPAC_FUSE_DS")) g_fuse_downsample = atoi(e) != 0;
+}
+
 static int init_driver_api() {
   if (g_encode_im2col && g_encode_tiled && g_num_sms) return 0;
   cudaDriverEntryPointQueryResult q;
@@ -363,9 +373,7 @@ static int init_driver_api() {
   int dev = 0;
   HIPAC_CHECK_CUDA(cudaGetDevice(&dev));
   HIPAC_CHECK_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
-  if (const char* e = getenv("HIPAC_CONV_ROWS")) g_use_row_kernels = atoi(e) != 0;
-  if (const char* e = getenv("HIPAC_FUSED_STEM")) g_use_fused_stem = atoi(e) != 0;
-  if (const char* e = getenv("HIPAC_FUSE_DS")) g_fuse_downsample = atoi(e) != 0;
+  read_env_flags();
   return 0;
 }
 
@@ -682,7 +690,10 @@ extern "C" int hipac_resnet18_pack(const float* const* t, int num_tensors, int n
 extern "C" size_t hipac_resnet18_workspace_bytes(int n_patches, int chunk) {
   if (n_patches <= 0) return 256;
   const size_t c = (size_t)clamp_chunk(chunk, n_patches);
-  return c * (kC1Bytes + 4 * kActBytes + kS2dBytes) + 6 * 1024;
+  read_env_flags();
+  // conv1's 112x112x64 output and the projection-shortcut tensor only exist in the unfused A/B modes; the S2D16
+  // repack buffer only when the caller hands the plain NHWC3 layout (sized for it unconditionally: 0.4 MB / patch)
+  return c * ((g_use_fused_stem ? 0 : kC1Bytes) + (g_fuse_downsample ? 3 : 4) * kActBytes + kS2dBytes) + 6 * 1024;
 }
 
 extern "C" int hipac_resnet18_conv_layer(const void* d_packed, int num_classes, int layer, const void* d_in,
@@ -735,11 +746,11 @@ extern "C" int hipac_resnet18_forward(const void* d_packed, int num_classes, con
     ws += align_up(bytes, 1024);
     return r;
   };
-  uint8_t* c1 = carve(cmax * kC1Bytes);
+  uint8_t* c1 = g_use_fused_stem ? nullptr : carve(cmax * kC1Bytes);
   uint8_t* A = carve(cmax * kActBytes);
   uint8_t* B = carve(cmax * kActBytes);
   uint8_t* C = carve(cmax * kActBytes);
-  uint8_t* D = carve(cmax * kActBytes);
+  uint8_t* D = g_fuse_downsample ? nullptr : carve(cmax * kActBytes);
   uint8_t* s2d = carve(cmax * kS2dBytes);
 
   for (int i0 = 0; i0 < n_patches; i0 += cmax) {

@@ -159,7 +159,7 @@ def extract_features_from_slides(level=3, model_path="resnet18_patch_classifier.
             i1 = min(ny, i0 + rows_per_slab)
             y0, y1 = i0 * S, min(height, (i1 - 1) * S + P)
             img = torch.from_numpy(np.ascontiguousarray(read_level_rows(slide, level, y0, y1))).to(device)
-            m = torch.from_numpy(np.ascontiguousarray(mask[y0:y1])).to(device) if mask is not None else None
+            m = torch.from_numpy(np.array(mask[y0:y1])).to(device) if mask is not None else None
             r = process_level(img, m, level, packed, stride=stride, row_range=(0, i1 - i0))
             c = r.coords.cpu().numpy().copy()
             c[:, 1] += y0

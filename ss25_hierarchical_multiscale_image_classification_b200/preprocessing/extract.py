@@ -95,7 +95,7 @@ def scan_slide(slide, level: int, mask: np.ndarray | None, stride=None, patch_si
         y0, y1 = i0 * S, min(height, (i1 - 1) * S + P)
         rgb = read_level_rows(slide, level, y0, y1)
         img = torch.from_numpy(np.ascontiguousarray(rgb)).to(device)
-        m = torch.from_numpy(np.ascontiguousarray(mask[y0:y1])).to(device) if mask is not None else None
+        m = torch.from_numpy(np.array(mask[y0:y1])).to(device) if mask is not None else None
         # a slab that ends above the image bottom has complete data for its grid rows, so tiling it as its own
         # image (rows [0, i1-i0) of the slab) gives exactly the patches of grid rows [i0, i1)
         pb = extract_patches_tensor(img, m, level, stride=stride, patch_size=patch_size, row_range=(0, i1 - i0),
