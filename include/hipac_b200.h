@@ -77,6 +77,13 @@ int hipac_tile_scan(const uint8_t* d_rgb, int H, int W, int64_t pitch_bytes,
                     void* d_workspace, size_t workspace_bytes,
                     int mode, void* stream);
 
+/* Early survivor count.  If a pinned host buffer int32[2] is registered (calling thread), every hipac_tile_scan copies
+ * {survivors, candidates} into it right after the compaction kernel and records an event; hipac_tile_scan_wait_count
+ * blocks only until that copy has landed -- the resample / gather kernels of the same call keep running, so the caller
+ * can enqueue the next stage without a pipeline bubble.  Pass NULL to unregister. */
+int hipac_tile_scan_set_count_buffer(int32_t* h_count_pinned);
+int hipac_tile_scan_wait_count(void);
+
 /* Pillow coefficient tables used by the kernels (known-answer hook for the CPU tests; no GPU needed).
  * scale in {2,4,8}; writes interior[2*scale], left_edge[3*scale/2], right_edge[3*scale/2] (22-bit fixed point). */
 int hipac_pillow_coeffs(int scale, int32_t* h_interior, int32_t* h_left, int32_t* h_right);

@@ -86,6 +86,10 @@ def _declare(l):
     l.hipac_tile_scan.restype = i32
     l.hipac_tile_scan.argtypes = [vp, i32, i32, i64, vp, i64, i32, i32, i32, i32, vp, vp, vp, vp, i32, vp, i32,
                                   vp, sz, i32, vp]
+    l.hipac_tile_scan_set_count_buffer.restype = i32
+    l.hipac_tile_scan_set_count_buffer.argtypes = [vp]
+    l.hipac_tile_scan_wait_count.restype = i32
+    l.hipac_tile_scan_wait_count.argtypes = []
     l.hipac_pillow_coeffs.restype = i32
     l.hipac_pillow_coeffs.argtypes = [i32, vp, vp, vp]
     l.hipac_normalize_lut_bf16.restype = i32
@@ -114,7 +118,7 @@ def _declare(l):
 
 EXPORTS = [
     "hipac_last_error", "hipac_abi_version", "hipac_launch_count", "hipac_tile_scan_workspace_bytes",
-    "hipac_tile_scan", "hipac_pillow_coeffs", "hipac_normalize_lut_bf16", "hipac_resnet18_packed_bytes",
+    "hipac_tile_scan", "hipac_tile_scan_set_count_buffer", "hipac_tile_scan_wait_count", "hipac_pillow_coeffs", "hipac_normalize_lut_bf16", "hipac_resnet18_packed_bytes",
     "hipac_resnet18_pack", "hipac_resnet18_workspace_bytes", "hipac_resnet18_forward",
     "hipac_resnet18_conv_layer", "hipac_profile_enable", "hipac_profile_report", "hipac_debug_umma_shift", "hipac_resnet18_stem", "hipac_resnet18_conv_ds_fused",
 ]

@@ -285,6 +285,20 @@ __global__ void __launch_bounds__(256) k_resample_direct(ScanParams p, OutParams
   write_s2d_pad(o, slot, j);
 }
 
+// Early publication of the survivor count: right after the compaction kernel the two counters are copied to a pinned
+// host buffer and an event is recorded, so the caller can size the next stage while the (much longer) resample /
+// gather kernels of this call are still running.
+static thread_local int32_t* g_count_host = nullptr;   // set by hipac_tile_scan_set_count_buffer
+static thread_local cudaEvent_t g_count_event = nullptr;
+
+static int publish_count(const int32_t* d_count, cudaStream_t stream) {
+  if (!g_count_host) return 0;
+  if (!g_count_event) HIPAC_CHECK_CUDA(cudaEventCreateWithFlags(&g_count_event, cudaEventDisableTiming));
+  HIPAC_CHECK_CUDA(cudaMemcpyAsync(g_count_host, d_count, 8, cudaMemcpyDeviceToHost, stream));
+  HIPAC_CHECK_CUDA(cudaEventRecord(g_count_event, stream));
+  return 0;
+}
+
 #include "tile_scan_fused.cuh"
 
 }  // namespace hipac
@@ -368,7 +382,7 @@ extern "C" int hipac_tile_scan(const uint8_t* d_rgb, int H, int W, int64_t pitch
 
   if (n_cand == 0) {
     HIPAC_CHECK_CUDA(cudaMemsetAsync(d_count, 0, 8, stream));
-    return 0;
+    return publish_count(d_count, stream);
   }
   FusedGeom geom;
   const bool fused_ok = n_cand > 0 && fused_geometry(p, &geom) && ((uintptr_t)d_rgb & 15) == 0;
@@ -386,6 +400,7 @@ extern "C" int hipac_tile_scan(const uint8_t* d_rgb, int H, int W, int64_t pitch
     k_compact<<<1, 1024, 0, stream>>>(p, flags, n_cand, d_coords, d_labels, src_idx, d_count, capacity, keep_all);
   }
   count_launch(2);
+  if (int e = publish_count(d_count, stream)) return e;
   if ((d_batch_u8 || d_batch) && capacity > 0) {
     dim3 grid((unsigned)min(n_cand, capacity), OUT);
     ProfileScope ps("resample_direct", stream, 0.0);
@@ -393,5 +408,16 @@ extern "C" int hipac_tile_scan(const uint8_t* d_rgb, int H, int W, int64_t pitch
     count_launch(1);
   }
   HIPAC_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int hipac_tile_scan_set_count_buffer(int32_t* h_count_pinned) {
+  g_count_host = h_count_pinned;
+  return 0;
+}
+
+extern "C" int hipac_tile_scan_wait_count(void) {
+  HIPAC_REQUIRE(g_count_host && g_count_event, "no count buffer registered or no scan issued on this thread");
+  HIPAC_CHECK_CUDA(cudaEventSynchronize(g_count_event));
   return 0;
 }

@@ -604,6 +604,7 @@ static int fused_scan_impl(const ScanParams& p, const OutParams& o, uint8_t* fla
     k_compact<<<1, 1024, 0, stream>>>(p, flags, n_cand, d_coords, d_labels, src_idx, d_count, capacity, keep_all);
   }
   count_launch(3);
+  if (int e = publish_count(d_count, stream)) return e;
   if ((o.batch_u8 || o.batch) && capacity > 0) {
     if (G.f == 2) {
       if (int e = launch_planes<2>(p, G, stream)) return e;

@@ -8,6 +8,7 @@ buffers and moves pointers.  There is no CPU fallback.
 """
 from __future__ import annotations
 
+import threading
 from dataclasses import dataclass
 
 import torch
@@ -20,6 +21,19 @@ S2D16_WIDTH = 115   # 112 + explicit zero columns (2 left, 1 right), include/hip
 
 _LAYOUTS = {"nhwc3": _lib.LAYOUT_NHWC3_BF16, "s2d16": _lib.LAYOUT_S2D16_BF16}
 _MODES = {"auto": _lib.SCAN_AUTO, "direct": _lib.SCAN_DIRECT, "fused": _lib.SCAN_FUSED}
+
+
+_count_host = threading.local()
+
+
+def _pinned_count():
+    """Per-thread pinned int32[2] registered with the library for the early survivor count."""
+    buf = getattr(_count_host, "buf", None)
+    if buf is None:
+        buf = torch.zeros(2, dtype=torch.int32).pin_memory()
+        _lib.check(_lib.lib().hipac_tile_scan_set_count_buffer(buf.data_ptr()), "hipac_tile_scan_set_count_buffer")
+        _count_host.buf = buf
+    return buf
 
 
 def patch_and_stride(level: int, stride=None, patch_size: int = 224):
@@ -65,7 +79,8 @@ def extract_patches_tensor(level_img: torch.Tensor, lesion_mask: torch.Tensor | 
     reference ``src/main.py:372-410``) or ``None`` -> every patch "normal" (``src/main.py:714-716``).
     ``row_range=(i0,i1)`` restricts to candidate grid rows ``y//stride in [i0,i1)`` -- the
     multi-GPU shard unit.  ``keep_all`` disables the tissue rejection (used on stacks of already
-    extracted patches).  Synchronises once to read the survivor count.
+    extracted patches).  Blocks only until the survivor count is known (after the compaction kernel); the
+    returned tensors are valid in stream order.
     """
     l = _lib.lib()
     if not (level_img.is_cuda and level_img.dtype == torch.uint8 and level_img.dim() == 3 and level_img.shape[2] == 3):
@@ -99,6 +114,7 @@ def extract_patches_tensor(level_img: torch.Tensor, lesion_mask: torch.Tensor | 
         if ws_bytes == 0:
             raise RuntimeError("hipac_tile_scan_workspace_bytes: " + l.hipac_last_error().decode())
         ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+        h_count = _pinned_count()
         rc = l.hipac_tile_scan(
             level_img.data_ptr(), H, W, pitch,
             lesion_mask.data_ptr() if lesion_mask is not None else None,
@@ -108,7 +124,11 @@ def extract_patches_tensor(level_img: torch.Tensor, lesion_mask: torch.Tensor | 
             batch.data_ptr() if batch is not None else None, _LAYOUTS[layout] if layout else 0,
             count.data_ptr(), cap, ws.data_ptr(), ws_bytes, m, st.cuda_stream)
         _lib.check(rc, "hipac_tile_scan")
-        n, n_c = (int(v) for v in count.cpu())
+        # wait only for the compaction (count copied to pinned memory); the resample / gather kernels keep running and
+        # everything enqueued next on this stream is ordered behind them
+        _lib.check(l.hipac_tile_scan_wait_count(), "hipac_tile_scan_wait_count")
+        n, n_c = int(h_count[0]), int(h_count[1])
+        ws.record_stream(st)
     if n > cap:
         raise RuntimeError(f"{n} survivors exceed capacity {cap}; pass a smaller row_range or a larger capacity")
     return PatchBatch(coords=coords[:n], labels=labels[:n], batch=batch[:n] if batch is not None else None,
