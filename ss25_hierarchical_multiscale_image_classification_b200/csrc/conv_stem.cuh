@@ -19,7 +19,7 @@ constexpr int kStemRegionLoad = kStemRows * kS2dW * 32;
 constexpr int kStemRegionBytes = (kStemRegionLoad + 128 * 32 + 1023) / 1024 * 1024;  // + slack for the 128-row UMMA window
 constexpr int kStemWBytes = 64 * 256 * 2;
 constexpr int kStemVBytes = 112 * 128;            // one conv row of bf16 [112][64]
-constexpr int kStemSmem = 2 * kStemRegionBytes + kStemWBytes + kStemVBytes + 1024 + 256;
+constexpr int kStemSmem = 2 * kStemRegionBytes + kStemWBytes + 2 * kStemVBytes + 1024 + 256;
 
 struct StemParams {
   int num_blocks;  // n_img * (56 / kStemPB)
@@ -49,8 +49,8 @@ k_conv1_pool(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = base;                                   // 2 block regions
   uint8_t* sW = base + 2 * kStemRegionBytes;            // resident weights, 4 k-blocks of [64 x 64] (128B swizzle)
-  uint8_t* sV = sW + kStemWBytes;                       // running vertical max [112][64] bf16, 16B chunks XOR-swizzled
-  uint64_t* a_full = reinterpret_cast<uint64_t*>(sV + kStemVBytes);
+  uint8_t* sV = sW + kStemWBytes;                       // 2 x completed vertical max [112][64] bf16 (16B chunks XOR-swizzled)
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(sV + 2 * kStemVBytes);
   uint64_t* a_empty = a_full + 2;
   uint64_t* w_full = a_empty + 2;
   uint64_t* tfull = w_full + 1;
@@ -135,7 +135,16 @@ k_conv1_pool(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     const int x = wq * 32 + lane;          // conv column of this thread's accumulator row
     const int et = threadIdx.x - 64;       // 0..255 among the epilogue threads
     const bool valid = x < 112;
-    uint32_t acc = 0, acc_phase = 0;
+    uint32_t acc = 0, acc_phase = 0, closings = 0;
+    // bias of this thread's 32 channels and the running vertical max of its conv column live in registers: the
+    // accumulator row of lane x is conv column x for EVERY tile, so the vertical 3-max never leaves the thread
+    float bias[32];
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + half * 32) + i);
+      bias[4 * i] = b.x, bias[4 * i + 1] = b.y, bias[4 * i + 2] = b.z, bias[4 * i + 3] = b.w;
+    }
+    __nv_bfloat162 vm[16];
     for (int blk = blockIdx.x; blk < p.num_blocks; blk += gridDim.x) {
       const int img = blk / BLOCKS_PER_IMG, py0 = (blk - img * BLOCKS_PER_IMG) * kStemPB;
       for (int t = (py0 == 0 ? 1 : 0); t <= 2 * kStemPB; t++) {
@@ -151,27 +160,24 @@ k_conv1_pool(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         if (lane == 0) ptx::mbar_arrive(&tempty[acc]);   // accumulator drained into registers
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
-        uint4 cur[4];  // this pixel's 32 channels, bf16
+        __nv_bfloat162 cur[16];  // this pixel's 32 channels: + folded-BN bias, ReLU, bf16
 #pragma unroll
-        for (int i = 0; i < 8; i++) {
-          const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + half * 32) + i);
-          const float y0 = fmaxf(__uint_as_float(v[4 * i + 0]) + b.x, 0.f), y1 = fmaxf(__uint_as_float(v[4 * i + 1]) + b.y, 0.f);
-          const float y2 = fmaxf(__uint_as_float(v[4 * i + 2]) + b.z, 0.f), y3 = fmaxf(__uint_as_float(v[4 * i + 3]) + b.w, 0.f);
-          __nv_bfloat162 lo = __floats2bfloat162_rn(y0, y1), hi = __floats2bfloat162_rn(y2, y3);
-          uint32_t* dst = reinterpret_cast<uint32_t*>(&cur[i >> 1]) + (i & 1) * 2;
-          dst[0] = *reinterpret_cast<uint32_t*>(&lo);
-          dst[1] = *reinterpret_cast<uint32_t*>(&hi);
-        }
-        uint4* mine = reinterpret_cast<uint4*>(sV + x * 128);
-        if (valid) {
+        for (int i = 0; i < 16; i++)
+          cur[i] = __floats2bfloat162_rn(fmaxf(__uint_as_float(v[2 * i]) + bias[2 * i], 0.f),
+                                         fmaxf(__uint_as_float(v[2 * i + 1]) + bias[2 * i + 1], 0.f));
 #pragma unroll
-          for (int j = 0; j < 4; j++) {
-            const int jj = (half * 4 + j) ^ (x & 7);  // XOR swizzle: conflict-free 16-byte accesses at a 128-byte row stride
-            mine[jj] = init ? cur[j] : bf16x8_max(mine[jj], cur[j]);
-          }
-        }
+        for (int i = 0; i < 16; i++) vm[i] = init ? cur[i] : __hmax2(vm[i], cur[i]);
         if (closes) {
-          // the running max is complete: horizontal 3-max, then restart it from this (shared) odd conv row
+          // vertical max complete: exchange through shared memory (double buffered: one barrier per pooled row),
+          // take the horizontal 3-max, then restart the running max from this (shared) odd conv row
+          uint8_t* buf = sV + (closings & 1) * kStemVBytes;
+          ++closings;
+          if (valid) {
+            uint4* mine = reinterpret_cast<uint4*>(buf + x * 128);
+#pragma unroll
+            for (int j = 0; j < 4; j++)   // XOR swizzle: conflict-free 16-byte accesses at a 128-byte row stride
+              mine[(half * 4 + j) ^ (x & 7)] = *reinterpret_cast<const uint4*>(&vm[4 * j]);
+          }
           named_bar_sync(1, 256);
           if (et < 224) {
             // thread -> (pooled column px, 16-channel quarter): 3-max over conv columns 2px-1, 2px, 2px+1
@@ -179,23 +185,20 @@ k_conv1_pool(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             const int py = py0 + (t >> 1) - 1;
             uint4 m[2];
 #pragma unroll
-            for (int j = 0; j < 2; j++) m[j] = reinterpret_cast<const uint4*>(sV + (2 * px) * 128)[(qtr * 2 + j) ^ ((2 * px) & 7)];
+            for (int j = 0; j < 2; j++) m[j] = reinterpret_cast<const uint4*>(buf + (2 * px) * 128)[(qtr * 2 + j) ^ ((2 * px) & 7)];
             if (px > 0) {
 #pragma unroll
               for (int j = 0; j < 2; j++)
-                m[j] = bf16x8_max(m[j], reinterpret_cast<const uint4*>(sV + (2 * px - 1) * 128)[(qtr * 2 + j) ^ ((2 * px - 1) & 7)]);
+                m[j] = bf16x8_max(m[j], reinterpret_cast<const uint4*>(buf + (2 * px - 1) * 128)[(qtr * 2 + j) ^ ((2 * px - 1) & 7)]);
             }
 #pragma unroll
             for (int j = 0; j < 2; j++)
-              m[j] = bf16x8_max(m[j], reinterpret_cast<const uint4*>(sV + (2 * px + 1) * 128)[(qtr * 2 + j) ^ ((2 * px + 1) & 7)]);
+              m[j] = bf16x8_max(m[j], reinterpret_cast<const uint4*>(buf + (2 * px + 1) * 128)[(qtr * 2 + j) ^ ((2 * px + 1) & 7)]);
             uint4* dst = reinterpret_cast<uint4*>(p.out + (((size_t)img * 56 + py) * 56 + px) * 64 + qtr * 16);
             dst[0] = m[0], dst[1] = m[1];
           }
-          named_bar_sync(1, 256);  // everyone has read its neighbours' columns
-          if (valid) {
 #pragma unroll
-            for (int j = 0; j < 4; j++) mine[(half * 4 + j) ^ (x & 7)] = cur[j];
-          }
+          for (int i = 0; i < 16; i++) vm[i] = cur[i];
         }
       }
     }
