@@ -364,17 +364,19 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    vals, last = [], None
+    vals, last, secs = [], None, []
     regions = cpu_sample_regions(args.cpu_candidates)
     for s in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
         r = cpu_baseline_sample(step=s, budget_candidates=args.cpu_candidates, regions=regions)
         if s >= args.warmup:
             vals.append(r)
+            secs.append(time.perf_counter() - t0)
         last = r
     tot_surv = sum(float(v["value"]) for v in vals) / len(vals)
     out = {"impl": "reference", "metric": "patches/sec (tile+mask+ResNet18 features)", "value": round(tot_surv, 2),
            "unit": "patches/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-           "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "ms_per_step": round(1e3 * sum(secs) / len(secs), 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "u8 + fp32 (CPU)", "data": "synthetic (same slide and weights as the GPU arm)",
            "config": {"workload": "configs[1] (bounded every-k-th-candidate sample per step), CPU port of the reference path",
                       "level": LEVEL, "patch": PATCH, "stride": STRIDE, "width": WIDTH, "rows_per_gpu": ROWS_PER_GPU},
