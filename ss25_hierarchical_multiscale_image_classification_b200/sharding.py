@@ -41,24 +41,46 @@ def gather_survivors(tensors: dict, group=None, sort: bool = True) -> dict:
 
     ``tensors`` maps names to tensors whose first dimension is this rank's survivor count (it must contain
     ``"coords"`` int32 ``[n,2]`` in GLOBAL level coordinates).  Every rank returns the concatenation over
-    ranks, in canonical ``(x, y)`` order when ``sort`` -- array-equal to a single-rank run."""
+    ranks, in canonical ``(x, y)`` order when ``sort`` -- array-equal to a single-rank run.
+
+    One exchange step: the per-survivor rows of all tensors are packed side by side into one byte matrix, so the
+    whole result travels in a single ``all_gather_into_tensor`` (after the tiny all-gather of the counts that
+    sizes the padding)."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     if world == 1:
         out = dict(tensors)
     else:
         ref = tensors["coords"]
-        n = torch.tensor([ref.shape[0]], dtype=torch.int64, device=ref.device)
-        counts = [torch.zeros_like(n) for _ in range(world)]
-        dist.all_gather(counts, n, group=group)
-        counts = [int(c) for c in counts]
-        mx = max(counts) if counts else 0
-        out = {}
-        for name, t in tensors.items():
-            pad = torch.zeros((mx,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
-            pad[: t.shape[0]] = t
-            buf = torch.empty((world * mx,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
-            dist.all_gather_into_tensor(buf, pad.contiguous(), group=group)
-            out[name] = torch.cat([buf[r * mx: r * mx + counts[r]] for r in range(world)])
+        dev, n = ref.device, int(ref.shape[0])
+        cnt = torch.tensor([n], dtype=torch.int64, device=dev)
+        counts = torch.empty((world,), dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(counts, cnt, group=group)
+        counts = counts.tolist()
+        mx = max(counts)
+        # pack: each tensor contributes (row bytes rounded up to 8) columns of a uint8 matrix
+        views, widths = [], []
+        for t in tensors.values():
+            rowb = t.element_size()
+            for d in t.shape[1:]:
+                rowb *= int(d)
+            flat = t.contiguous().reshape(n, -1).view(torch.uint8) if n else None
+            views.append((flat, rowb))
+            widths.append((rowb + 7) // 8 * 8)
+        packed = torch.zeros((mx, sum(widths)), dtype=torch.uint8, device=dev)
+        off = 0
+        for (flat, rowb), w in zip(views, widths):
+            if n:
+                packed[:n, off:off + rowb] = flat.reshape(n, rowb)
+            off += w
+        buf = torch.empty((world * mx, sum(widths)), dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(buf, packed, group=group)
+        rows = torch.cat([buf[r * mx: r * mx + counts[r]] for r in range(world)]) if world > 1 else buf[:n]
+        out, off = {}, 0
+        total = rows.shape[0]
+        for (name, t), (_, rowb), w in zip(tensors.items(), views, widths):
+            col = rows[:, off:off + rowb].contiguous()
+            out[name] = col.view(t.dtype).reshape((total,) + tuple(t.shape[1:]))
+            off += w
     if sort and out["coords"].shape[0]:
         perm = canonical_order(out["coords"])
         out = {k: v[perm] for k, v in out.items()}
