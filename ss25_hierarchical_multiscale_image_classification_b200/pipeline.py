@@ -31,15 +31,38 @@ class LevelResult:
         return int(self.coords.shape[0])
 
 
-def process_level(level_img: torch.Tensor, lesion_mask, level: int, packed: _features.PackedResNet18, stride=None,
-                  row_range=None, chunk: int = 4096, mode: str = "auto") -> LevelResult:
-    """Tile + tissue/lesion mask + ResNet18 features of a level image resident on the GPU."""
-    pb = extract_patches_tensor(level_img, lesion_mask, level, stride=stride, row_range=row_range, layout="s2d16", mode=mode)
+def _process_rows(level_img, lesion_mask, level, packed, stride, rows, chunk, mode):
+    pb = extract_patches_tensor(level_img, lesion_mask, level, stride=stride, row_range=rows, layout="s2d16", mode=mode)
     if packed.num_classes > 0:
         feats, logits = _features.classify_tensor(pb.batch, packed, chunk)
     else:
         feats, logits = _features.extract_features_tensor(pb.batch, packed, chunk), None
     return LevelResult(pb.coords, pb.labels, feats, logits, pb.candidates)
+
+
+def process_level(level_img: torch.Tensor, lesion_mask, level: int, packed: _features.PackedResNet18, stride=None,
+                  row_range=None, chunk: int = 4096, mode: str = "auto", max_candidates: int = 16384) -> LevelResult:
+    """Tile + tissue/lesion mask + ResNet18 features of a level image resident on the GPU.
+
+    The batch buffer is sized for the worst case (every candidate survives), so levels with more than
+    ``max_candidates`` candidates are processed in groups of whole candidate-grid rows (a 100k x 100k level at
+    224-px tiles has 200k candidates = 82 GB of batch at once); the result is returned in canonical ``(x, y)``
+    order either way."""
+    H, W = int(level_img.shape[0]), int(level_img.shape[1])
+    P, S = patch_and_stride(level, stride)
+    nx, ny_all = grid_shape(W, H, S)
+    i0, i1 = (0, ny_all) if row_range is None else (int(row_range[0]), int(row_range[1]))
+    rows_per_group = max(1, max_candidates // max(nx, 1))
+    if i1 - i0 <= rows_per_group:
+        return _process_rows(level_img, lesion_mask, level, packed, stride, (i0, i1), chunk, mode)
+    parts = [_process_rows(level_img, lesion_mask, level, packed, stride, (a, min(a + rows_per_group, i1)), chunk, mode)
+             for a in range(i0, i1, rows_per_group)]
+    coords = torch.cat([r.coords for r in parts])
+    key = coords[:, 0].to(torch.int64) * (1 << 32) + coords[:, 1].to(torch.int64)
+    perm = torch.argsort(key, stable=True)
+    logits = torch.cat([r.logits for r in parts])[perm] if parts[0].logits is not None else None
+    return LevelResult(coords[perm], torch.cat([r.labels for r in parts])[perm], torch.cat([r.features for r in parts])[perm],
+                       logits, sum(r.candidates for r in parts))
 
 
 class HostPipeline:

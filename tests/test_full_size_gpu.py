@@ -84,3 +84,18 @@ def test_all_levels_pyramid_and_heatmap():
             for (x, y), pr in zip(want["coords"], ref_p):
                 assert abs(grid[y // 224, x // 224] - pr) < 2e-2
             assert (grid >= 0).sum() == len(r)
+
+
+def test_process_level_in_row_groups_equals_single_shot():
+    """Levels too large for one worst-case batch are processed in candidate-row groups: same result, same order."""
+    from ss25_hierarchical_multiscale_image_classification_b200 import features, pipeline
+    from ss25_hierarchical_multiscale_image_classification_b200.synthetic import SyntheticSlide
+    slide = SyntheticSlide(20000, 16000, seed=9)
+    img = torch.from_numpy(slide.level_array(3)).cuda()
+    msk = torch.from_numpy(slide.lesion_mask(3)).cuda()
+    packed = features.pack_resnet18(orc.make_resnet18(seed=0, classifier=True).state_dict(), "cuda")
+    one = pipeline.process_level(img, msk, 3, packed)
+    many = pipeline.process_level(img, msk, 3, packed, max_candidates=40)      # 12 candidate columns -> 3 rows per group
+    assert many.candidates == one.candidates and len(one) > 10
+    assert torch.equal(many.coords, one.coords) and torch.equal(many.labels, one.labels)
+    assert torch.equal(many.features, one.features) and torch.equal(many.logits, one.logits)
