@@ -38,6 +38,8 @@ extern "C" {
 #define HIPAC_SCAN_AUTO   0 /* fused read-once path when stride %% (P/224) == 0, else direct */
 #define HIPAC_SCAN_DIRECT 1 /* one window reduction + one resample per patch (any stride) */
 #define HIPAC_SCAN_FUSED  2 /* single streaming pass over the level image (error if not applicable) */
+#define HIPAC_SCAN_NO_STREAM 0x200 /* OR-able flag: run the fused path with its cp.async kernels (two reads of the image) instead of the
+                                      TMA streaming pass; the two are bit-identical, the flag exists for the cross-check tests */
 #define HIPAC_SCAN_KEEP_ALL 0x100 /* OR-able flag: skip the tissue rejection (every candidate survives); used when the input
                                      is a stack of already-extracted patches, as in the reference's extract_features */
 

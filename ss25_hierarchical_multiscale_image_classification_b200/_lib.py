@@ -20,6 +20,7 @@ LAYOUT_NHWC3_BF16 = 1
 LAYOUT_S2D16_BF16 = 2
 SCAN_AUTO, SCAN_DIRECT, SCAN_FUSED = 0, 1, 2
 SCAN_KEEP_ALL = 0x100
+SCAN_NO_STREAM = 0x200
 RESNET18_NUM_CONVS = 20
 
 _lock = threading.Lock()

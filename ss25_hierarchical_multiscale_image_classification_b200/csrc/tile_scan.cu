@@ -5,6 +5,7 @@
 #include "common.cuh"
 #include "pillow_coeffs.h"
 #include "tile_scan_shared.cuh"
+#include "umma.cuh"
 
 namespace hipac {
 
@@ -334,7 +335,7 @@ static int scan_geometry(int H, int W, int P, int S, int iy_begin, int iy_end, i
 }
 
 extern "C" size_t hipac_tile_scan_workspace_bytes(int H, int W, int P, int S, int iy_begin, int iy_end, int mode) {
-  mode &= ~HIPAC_SCAN_KEEP_ALL;
+  mode &= ~(HIPAC_SCAN_KEEP_ALL | HIPAC_SCAN_NO_STREAM);
   int nx, ny;
   if (scan_geometry(H, W, P, S, iy_begin, iy_end, &nx, &ny)) return 0;
   const size_t n_cand = (size_t)nx * ny;
@@ -353,7 +354,8 @@ extern "C" int hipac_tile_scan(const uint8_t* d_rgb, int H, int W, int64_t pitch
                                int capacity, void* d_workspace, size_t workspace_bytes, int mode, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   const int keep_all = (mode & HIPAC_SCAN_KEEP_ALL) ? 1 : 0;
-  mode &= ~HIPAC_SCAN_KEEP_ALL;
+  g_stream_disable = (mode & HIPAC_SCAN_NO_STREAM) ? 1 : 0;
+  mode &= ~(HIPAC_SCAN_KEEP_ALL | HIPAC_SCAN_NO_STREAM);
   int nx, ny;
   if (int e = scan_geometry(H, W, P, S, iy_begin, iy_end, &nx, &ny)) return e;
   HIPAC_REQUIRE(d_rgb && d_coords && d_labels && d_count && d_workspace, "null pointer");

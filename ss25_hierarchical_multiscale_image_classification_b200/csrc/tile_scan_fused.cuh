@@ -90,7 +90,7 @@ static size_t fused_workspace_bytes_impl(const ScanParams& p) {
 // ------------------------------------------------------------------------------------------
 // pass A1: per-cell byte sums and lesion votes (32-row bands, one warp per row)
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_cell_stats(ScanParams p, FusedGeom G) {
+__global__ void __launch_bounds__(256) k_cell_stats(ScanParams p, FusedGeom G, int do_rgb) {
   const int cx = blockIdx.x;
   const int r0 = G.cy0 * G.g + blockIdx.y * 32;
   if (r0 >= p.H) return;
@@ -99,8 +99,9 @@ __global__ void __launch_bounds__(256) k_cell_stats(ScanParams p, FusedGeom G) {
   const int xb = cx * G.g, xe = min(p.W, xb + G.g);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint32_t s = 0, any = 0;
-  const int nbytes = (xe - xb) * 3;
-  if ((p.pitch & 15) == 0 && ((reinterpret_cast<uintptr_t>(p.rgb) + (size_t)xb * 3) & 15) == 0) {
+  const int nbytes = do_rgb ? (xe - xb) * 3 : 0;
+  if (!do_rgb) {
+  } else if ((p.pitch & 15) == 0 && ((reinterpret_cast<uintptr_t>(p.rgb) + (size_t)xb * 3) & 15) == 0) {
     // fast path: every row of the band starts 16-byte aligned -> flatten (row, chunk) over the CTA and keep
     // several independent 128-bit loads in flight per thread
     const int nfull = nbytes >> 4, nrows = r1 - r0, total = nrows * nfull;
@@ -147,7 +148,7 @@ __global__ void __launch_bounds__(256) k_cell_stats(ScanParams p, FusedGeom G) {
   if (threadIdx.x == 0) {
     uint32_t tot = 0, a = 0;
     for (int w = 0; w < 8; w++) tot += sh_s[w], a |= sh_a[w];
-    atomicAdd(&G.cell_sum[(size_t)cyl * G.ncx + cx], tot);  // cell total <= 1792^2*3*255 < 2^32
+    if (tot) atomicAdd(&G.cell_sum[(size_t)cyl * G.ncx + cx], tot);  // cell total <= 1792^2*3*255 < 2^32
     if (a) atomicOr(&G.cell_any[(size_t)cyl * G.ncx + cx], 1u);
   }
 }
@@ -551,6 +552,8 @@ __global__ void __launch_bounds__(128) k_gather(ScanParams p, FusedGeom G, OutPa
   }
 }
 
+#include "tile_scan_stream.cuh"
+
 // ------------------------------------------------------------------------------------------
 // host driver
 // ------------------------------------------------------------------------------------------
@@ -571,6 +574,53 @@ static int launch_planes(const ScanParams& p, const FusedGeom& G, cudaStream_t s
   return 0;
 }
 
+// ---- streaming pass (tile_scan_stream.cuh) ----
+static thread_local int g_stream_disable = 0;   // HIPAC_SCAN_NO_STREAM: force the cp.async kernels (cross-check)
+
+static bool stream_applicable(const ScanParams& p, const FusedGeom& G) {
+  if (g_stream_disable || G.f == 1) return false;
+  if ((p.pitch & 15) || (reinterpret_cast<uintptr_t>(p.rgb) & 15)) return false;
+  if (G.Sf < 2) return false;
+  const int cols = kStripUnits * (8 / G.f);
+  if (2 * ((cols + G.Sf - 1) / G.Sf + 1) > kStreamMaxVar) return false;
+  return true;
+}
+
+template <int F>
+static int launch_scan_planes_f(const ScanParams& p, const FusedGeom& G, cudaStream_t stream) {
+  const size_t smem = (size_t)kStreamWarps * kStreamStages * (kStreamRows * kStreamRowBytes + 8);
+  static int sms = 0, per_sm = 0;
+  if (!sms) {
+    int dev = 0;
+    HIPAC_CHECK_CUDA(cudaGetDevice(&dev));
+    HIPAC_CHECK_CUDA(cudaFuncSetAttribute(k_scan_planes<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    HIPAC_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_scan_planes<F>, kStreamWarps * 32, smem));
+    HIPAC_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    if (per_sm < 1) per_sm = 1;
+  }
+  StreamGeom Z;
+  Z.n_strips = (G.Dw + kStripUnits * (8 / F) - 1) / (kStripUnits * (8 / F));
+  // one resident wave: every warp slot of the GPU gets at most one (strip, row chunk) item of equal height
+  const int slots = sms * per_sm * kStreamWarps;
+  Z.n_chunks = slots / Z.n_strips;
+  if (Z.n_chunks < 1) Z.n_chunks = 1;
+  const int min_rows = 4;   // D rows per item: below this the one-block overlap between chunks dominates
+  if (Z.n_chunks > (G.Dh + min_rows - 1) / min_rows) Z.n_chunks = (G.Dh + min_rows - 1) / min_rows;
+  Z.srow_lo = G.cy0 * G.g;
+  Z.srow_hi = min(p.H, (G.cy0 + G.ncy) * G.g);
+  const int items = Z.n_strips * Z.n_chunks;
+  ProfileScope ps("scan_planes", stream, (double)p.H * p.W * 3);
+  k_scan_planes<F><<<(items + kStreamWarps - 1) / kStreamWarps, kStreamWarps * 32, smem, stream>>>(p, G, Z);
+  count_launch(1);
+  return 0;
+}
+
+static int launch_scan_planes(const ScanParams& p, const FusedGeom& G, cudaStream_t stream) {
+  if (G.f == 2) return launch_scan_planes_f<2>(p, G, stream);
+  if (G.f == 4) return launch_scan_planes_f<4>(p, G, stream);
+  return launch_scan_planes_f<8>(p, G, stream);
+}
+
 static int fused_scan_impl(const ScanParams& p, const OutParams& o, uint8_t* flags, int32_t* src_idx, int32_t* d_coords,
                            uint8_t* d_labels, int32_t* d_count, int capacity, uint8_t* ws, cudaStream_t stream, int keep_all) {
   FusedGeom G;
@@ -589,11 +639,17 @@ static int fused_scan_impl(const ScanParams& p, const OutParams& o, uint8_t* fla
     }
   const int n_cand = p.nx * p.ny;
   HIPAC_CHECK_CUDA(cudaMemsetAsync(G.cell_sum, 0, 2 * cell_bytes, stream));
-  {
+  const bool stream_ok = stream_applicable(p, G);
+  if (stream_ok) {
+    // one read of the image: cell sums + resampled planes; the lesion votes come from a mask-only pass
+    if (int e = launch_scan_planes(p, G, stream)) return e;
+  }
+  if (!stream_ok || p.mask) {
     const int rows = min(p.H, (G.cy0 + G.ncy) * G.g) - G.cy0 * G.g;
     dim3 grid(G.ncx, (rows + 31) / 32);
-    ProfileScope ps("cell_stats", stream, (double)rows * p.W * (p.mask ? 4 : 3));
-    k_cell_stats<<<grid, 256, 0, stream>>>(p, G);
+    ProfileScope ps(stream_ok ? "cell_votes" : "cell_stats", stream, (double)rows * p.W * ((p.mask ? 1 : 0) + (stream_ok ? 0 : 3)));
+    k_cell_stats<<<grid, 256, 0, stream>>>(p, G, stream_ok ? 0 : 1);
+    count_launch(1);
   }
   {
     ProfileScope ps("patch_flags", stream, 0.0);
@@ -603,10 +659,12 @@ static int fused_scan_impl(const ScanParams& p, const OutParams& o, uint8_t* fla
     ProfileScope ps("compact", stream, (double)n_cand);
     k_compact<<<1, 1024, 0, stream>>>(p, flags, n_cand, d_coords, d_labels, src_idx, d_count, capacity, keep_all);
   }
-  count_launch(3);
+  count_launch(2);
   if (int e = publish_count(d_count, stream)) return e;
   if ((o.batch_u8 || o.batch) && capacity > 0) {
-    if (G.f == 2) {
+    if (stream_ok) {
+      // planes already written by the streaming pass
+    } else if (G.f == 2) {
       if (int e = launch_planes<2>(p, G, stream)) return e;
     } else if (G.f == 4) {
       if (int e = launch_planes<4>(p, G, stream)) return e;

@@ -20,7 +20,8 @@ OUT = 224
 S2D16_WIDTH = 115   # 112 + explicit zero columns (2 left, 1 right), include/hipac_b200.h
 
 _LAYOUTS = {"nhwc3": _lib.LAYOUT_NHWC3_BF16, "s2d16": _lib.LAYOUT_S2D16_BF16}
-_MODES = {"auto": _lib.SCAN_AUTO, "direct": _lib.SCAN_DIRECT, "fused": _lib.SCAN_FUSED}
+_MODES = {"auto": _lib.SCAN_AUTO, "direct": _lib.SCAN_DIRECT, "fused": _lib.SCAN_FUSED,
+          "fused_legacy": _lib.SCAN_FUSED | _lib.SCAN_NO_STREAM}   # cp.async kernels instead of the TMA streaming pass
 
 
 _count_host = threading.local()

@@ -12,10 +12,24 @@ torch = pytest.importorskip("torch")
 pytestmark = pytest.mark.gpu
 
 
-def _run(level_img, mask, level, stride, mode="auto", layout="nhwc3", row_range=None):
+def _pitched(a):
+    """Device copy of a [H,W,(3)] array whose row pitch is a multiple of 16 bytes (a view into a wider buffer): the
+    layout the TMA streaming pass needs, with an arbitrary image width."""
+    h, w = a.shape[:2]
+    wp = (w + 15) // 16 * 16 + 16
+    buf = torch.full((h, wp) + tuple(a.shape[2:]), 77, dtype=torch.uint8, device="cuda")   # padding bytes are garbage
+    buf[:, :w] = torch.from_numpy(a).cuda()
+    return buf[:, :w]
+
+
+def _run(level_img, mask, level, stride, mode="auto", layout="nhwc3", row_range=None, pitched=False):
     from ss25_hierarchical_multiscale_image_classification_b200.preprocessing import extract_patches_tensor
-    img = torch.from_numpy(level_img).cuda()
-    m = torch.from_numpy(mask).cuda() if mask is not None else None
+    if pitched:
+        img = _pitched(level_img)
+        m = _pitched(mask) if mask is not None else None
+    else:
+        img = torch.from_numpy(level_img).cuda()
+        m = torch.from_numpy(mask).cuda() if mask is not None else None
     return extract_patches_tensor(img, m, level, stride=stride, layout=layout, want_u8=True, mode=mode,
                                   row_range=row_range)
 
@@ -136,3 +150,46 @@ def test_fused_mode_rejects_unaligned_stride():
     img = np.full((1000, 1000, 3), 100, np.uint8)
     with pytest.raises(RuntimeError, match="fused scan needs"):
         _run(img, None, 1, 300, mode="fused")
+
+
+@pytest.mark.parametrize("level,stride,w,h", [(0, None, 3100, 2600), (1, None, 3111, 2637), (2, None, 3122, 2674), (0, 1792, 4000, 3700),
+                                               (1, 896, 2100, 1900), (2, 448, 1500, 1100), (1, 448, 2100, 1900), (0, 256, 2500, 2300),
+                                               (2, None, 449, 225), (1, None, 100, 90), (0, None, 8, 3000), (2, 32, 700, 600),
+                                               (0, None, 5953, 1800), (0, None, 5955, 1796), (1, None, 2977, 1000)])
+@pytest.mark.parametrize("with_mask", [True, False])
+def test_streaming_pass_equals_direct_and_legacy_bitwise(level, stride, w, h, with_mask):
+    """The TMA streaming pass (one read: cell sums + planes) vs the per-patch path and the cp.async kernels, on
+    16-byte-pitched images of arbitrary width (strip edges, white padding, partial cells, tiny images)."""
+    rng = np.random.default_rng(level * 100 + w)
+    img = rng.integers(150, 256, size=(h, w, 3), dtype=np.uint8)
+    img[h // 8: 3 * h // 4, w // 6: 5 * w // 6] = rng.integers(0, 256, size=(3 * h // 4 - h // 8, 5 * w // 6 - w // 6, 3), dtype=np.uint8)
+    mask = None
+    if with_mask:
+        mask = np.zeros((h, w), np.uint8)
+        mask[h // 3: h // 3 + 20, w // 4: w // 2] = 7
+        mask[h - 1, w - 1] = 1
+    a = _run(img, mask, level, stride, mode="direct", layout="s2d16")
+    b = _run(img, mask, level, stride, mode="fused", layout="s2d16", pitched=True)
+    c = _run(img, mask, level, stride, mode="fused_legacy", layout="s2d16", pitched=True)
+    for o in (b, c):
+        assert a.candidates == o.candidates and len(a) == len(o)
+        assert torch.equal(a.coords, o.coords) and torch.equal(a.labels, o.labels)
+        assert torch.equal(a.images_u8, o.images_u8)
+        assert torch.equal(a.batch.view(torch.int16), o.batch.view(torch.int16))
+
+
+def test_streaming_pass_row_range_shards():
+    """Row-range shards of the streaming pass concatenate (in canonical order) to the full scan."""
+    rng = np.random.default_rng(5)
+    h, w = 5000, 2400
+    img = rng.integers(120, 256, size=(h, w, 3), dtype=np.uint8)
+    mask = np.zeros((h, w), np.uint8)
+    mask[2000:2100, 300:900] = 255
+    full = _run(img, mask, 1, None, mode="fused", pitched=True)
+    ny = (h + 223) // 224
+    parts = [_run(img, mask, 1, None, mode="fused", pitched=True, row_range=r) for r in [(0, 5), (5, 6), (6, ny)]]
+    coords = torch.cat([q.coords for q in parts]).cpu().numpy()
+    order = np.lexsort((coords[:, 1], coords[:, 0]))
+    assert np.array_equal(coords[order], full.coords.cpu().numpy())
+    assert np.array_equal(torch.cat([q.labels for q in parts]).cpu().numpy()[order], full.labels.cpu().numpy())
+    assert np.array_equal(torch.cat([q.images_u8 for q in parts]).cpu().numpy()[order], full.images_u8.cpu().numpy())
