@@ -15,6 +15,7 @@ namespace hipac {
 __constant__ CoeffSet c_coef[4];          // index log2(scale); [0] unused
 __constant__ uint16_t c_lut_bf16[768];    // [v][c] -> bf16 bits of (v/255 - mean_c)/std_c
 __device__ uint16_t g_lut_bf16[768];      // same table in global memory (gathered with divergent indices)
+__constant__ float c_norm_a[3], c_norm_b[3];   // y = fma(v, a_c, b_c): one-instruction form of the table (checked at start-up)
 
 static const float kMean[3] = {0.485f, 0.456f, 0.406f};  // reference src/main.py:816
 static const float kStd[3] = {0.229f, 0.224f, 0.225f};
@@ -52,6 +53,20 @@ static int upload_constants(cudaStream_t stream) {
     for (int t = 0; t < 12; t++) h_coef[l].left[t] = pc.left[t], h_coef[l].right[t] = pc.right[t];
   }
   host_normalize_lut_bf16(h_lut);
+  // single-FMA form of ToTensor+Normalize used by the gather kernel; it must reproduce the table bit for bit
+  float h_a[3], h_b[3];
+  for (int c = 0; c < 3; c++) {
+    h_a[c] = (float)(1.0 / (255.0 * (double)kStd[c]));
+    h_b[c] = (float)(-(double)kMean[c] / (double)kStd[c]);
+    for (int v = 0; v < 256; v++) {
+      if (f32_to_bf16_rne(fmaf((float)v, h_a[c], h_b[c])) != h_lut[v * 3 + c]) {
+        set_error("single-FMA normalisation does not reproduce the fp32 ToTensor/Normalize table");
+        return -3;
+      }
+    }
+  }
+  HIPAC_CHECK_CUDA(cudaMemcpyToSymbolAsync(c_norm_a, h_a, sizeof(h_a), 0, cudaMemcpyHostToDevice, stream));
+  HIPAC_CHECK_CUDA(cudaMemcpyToSymbolAsync(c_norm_b, h_b, sizeof(h_b), 0, cudaMemcpyHostToDevice, stream));
   HIPAC_CHECK_CUDA(cudaMemcpyToSymbolAsync(c_coef, h_coef, sizeof(h_coef), 0, cudaMemcpyHostToDevice, stream));
   HIPAC_CHECK_CUDA(cudaMemcpyToSymbolAsync(c_lut_bf16, h_lut, sizeof(h_lut), 0, cudaMemcpyHostToDevice, stream));
   HIPAC_CHECK_CUDA(cudaMemcpyToSymbolAsync(g_lut_bf16, h_lut, sizeof(h_lut), 0, cudaMemcpyHostToDevice, stream));
@@ -364,6 +379,7 @@ extern "C" int hipac_tile_scan(const uint8_t* d_rgb, int H, int W, int64_t pitch
   HIPAC_REQUIRE(capacity >= 0, "negative capacity");
   HIPAC_REQUIRE(!d_batch || layout == HIPAC_LAYOUT_NHWC3_BF16 || layout == HIPAC_LAYOUT_S2D16_BF16, "unknown batch layout");
   HIPAC_REQUIRE(((uintptr_t)d_workspace & 255) == 0, "workspace must be 256-byte aligned");
+  HIPAC_REQUIRE(((uintptr_t)d_batch_u8 & 15) == 0 && ((uintptr_t)d_batch & 31) == 0, "batch buffers must be 16/32-byte aligned");
   HIPAC_REQUIRE(workspace_bytes >= hipac_tile_scan_workspace_bytes(H, W, P, S, iy_begin, iy_end, mode), "workspace too small");
   HIPAC_REQUIRE((int64_t)nx * ny < (int64_t)1 << 30, "too many candidates for one call; split the row range");
   HIPAC_REQUIRE(mode == HIPAC_SCAN_AUTO || mode == HIPAC_SCAN_DIRECT || mode == HIPAC_SCAN_FUSED, "unknown scan mode");

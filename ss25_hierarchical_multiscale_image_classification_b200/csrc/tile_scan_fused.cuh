@@ -427,127 +427,149 @@ __global__ void __launch_bounds__(256) k_downsample_planes(ScanParams p, FusedGe
 
 // ------------------------------------------------------------------------------------------
 constexpr int kGatherPairs = 8;                 // output row pairs per CTA (112 = 14 * 8)
-constexpr int kGatherRowCap = OUT * 3 + 16;     // 672 row bytes + alignment phase, multiple of 16
-
-// Source of output row j of a patch: pointer to the 672 contiguous bytes of its interior columns (or null when the
-// whole row is white), number of valid leading bytes, and the two ring pixels that come from the clamp planes.
-struct GatherRow {
-  const uint8_t* src;     // byte 0 = output column 0 (interior plane / image row), may be unaligned
-  int valid;              // bytes [0, valid) exist in the source; the rest is white (255)
-  const uint8_t* left;    // 3 bytes for output column 0, or null (use src)
-  const uint8_t* right;   // 3 bytes for output column 223, or null (use src)
-};
-
-__device__ __forceinline__ GatherRow gather_row(const ScanParams& p, const FusedGeom& G, int x, int y, int iyl, int j) {
-  GatherRow g;
-  g.left = g.right = nullptr;
-  if (G.f == 1) {
-    const int yy = y + j;
-    g.src = yy < p.H ? p.rgb + (int64_t)yy * p.pitch + (int64_t)x * 3 : nullptr;
-    g.valid = yy < p.H ? min(OUT, p.W - x) * 3 : 0;
-    return g;
-  }
-  const int J = y / G.f + j - G.Jbase, I0 = x / G.f;
-  if (J >= G.Dh) {  // vertical window entirely in the white padding
-    g.src = nullptr, g.valid = 0;
-    return g;
-  }
-  const int vk = j == 0 ? 1 : (j == OUT - 1 ? 2 : 0);
-  const size_t row = vk == 0 ? (size_t)J : (size_t)iyl;
-  g.src = G.plane[vk][0] + (row * G.Dw + I0) * 3;
-  g.valid = max(0, min(OUT, G.Dw - I0)) * 3;
-  const size_t ix = (size_t)(x / p.S);
-  g.left = G.plane[vk][1] + (row * G.nx + ix) * 3;                       // column I0 always exists (x < W)
-  g.right = I0 + OUT - 1 < G.Dw ? G.plane[vk][2] + (row * G.nx + ix) * 3 : nullptr;   // else white via `valid`
-  return g;
-}
 
 // pass B: gather the 224 x 224 crop of every survivor from the planes (or the image when f == 1).
-//   grid (survivor slot, 14 groups of 8 row pairs).  Each warp copies whole source rows into shared memory with
-//   aligned 32-bit loads (the row keeps its global alignment phase), patches the two ring pixels, then thread X
-//   of a row pair produces the 2x2 output pixels (2*jp+dy, 2*X+dx) = one 32-byte space-to-depth pixel.
+//   grid (survivor slot, 14 groups of 8 row pairs), 128 threads.  Thread X < 112 owns output columns 2X, 2X+1: per row
+//   it reads its 6 source bytes with three aligned 32-bit loads (a warp covers 192 contiguous bytes; the planes are L2
+//   resident), funnel-shifts the alignment away, patches the ring pixels (columns 0 / 223 come from the clamp planes)
+//   and the white padding, and writes one 32-byte space-to-depth pixel per row pair.  ToTensor + Normalize is one FFMA
+//   per value (c_norm_a/c_norm_b, verified at start-up to reproduce the reference's fp32 div/sub/div chain in every one
+//   of the 768 (value, channel) cases after bf16 rounding).  No shared memory, no block barrier.
+__device__ __forceinline__ float byte_to_float(uint32_t w, int i) {
+  // 0x4B0000bb is the float 2^23 + bb: exact uint8 -> float without an integer-to-float conversion
+  return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7540u + i)) - 8388608.0f;
+}
+__device__ __forceinline__ uint32_t norm_pack(uint32_t w, int i0, int c0, int i1, int c1) {
+  const float lo = fmaf(byte_to_float(w, i0), c_norm_a[c0], c_norm_b[c0]);
+  const float hi = fmaf(byte_to_float(w, i1), c_norm_a[c1], c_norm_b[c1]);
+  const __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t*>(&v);
+}
+
+// one 32-byte space-to-depth pixel with a single 256-bit store (sm_100: STG.256), so every L2 sector is written whole
+__device__ __forceinline__ void st_global_256(void* dst, const uint4& lo, const uint4& hi) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst), "r"(lo.x), "r"(lo.y), "r"(lo.z), "r"(lo.w), "r"(hi.x),
+               "r"(hi.y), "r"(hi.z), "r"(hi.w)
+               : "memory");
+}
+
+template <bool F1>
 __global__ void __launch_bounds__(128) k_gather(ScanParams p, FusedGeom G, OutParams o, const int32_t* __restrict__ coords,
                                                 const int32_t* __restrict__ count, int capacity) {
   const int slot = blockIdx.x, jp0 = blockIdx.y * kGatherPairs;
   if (slot >= min(count[0], capacity)) return;
-  __shared__ __align__(16) uint8_t rowbuf[2 * kGatherPairs][kGatherRowCap];
-  __shared__ int rowphase[2 * kGatherPairs];
-  __shared__ uint16_t lut[768];
+  __shared__ uint32_t ring[2 * kGatherPairs][2];   // ring pixels (3 bytes) of the CTA's 16 rows: [row][left, right]
   const int x = coords[2 * slot], y = coords[2 * slot + 1];
-  const int iyl = y / p.S - p.iy_begin;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  for (int e = tid; e < 384; e += 128) reinterpret_cast<uint32_t*>(lut)[e] = reinterpret_cast<const uint32_t*>(g_lut_bf16)[e];
-  for (int rr = warp; rr < 2 * kGatherPairs; rr += 4) {
-    const GatherRow g = gather_row(p, G, x, y, iyl, 2 * jp0 + rr);
-    const int phase = g.src ? (int)(reinterpret_cast<uintptr_t>(g.src) & 3) : 0;
-    uint32_t* dst = reinterpret_cast<uint32_t*>(rowbuf[rr]);
-    const int nwords = (phase + g.valid + 3) >> 2;                       // aligned words covering the valid bytes
-    const uint32_t* srcw = reinterpret_cast<const uint32_t*>(g.src - phase);
-    // words that would cross the end of the level image (only possible for f == 1, last row) are assembled bytewise
-    const uint8_t* img_end = p.rgb + (int64_t)p.H * p.pitch;
-    for (int k = lane; k < kGatherRowCap / 4; k += 32) {
-      uint32_t v = 0xFFFFFFFFu;
-      if (k < nwords) {
-        const uint8_t* a = reinterpret_cast<const uint8_t*>(srcw + k);
-        if (G.f != 1 || a + 4 <= img_end) {
-          v = __ldg(srcw + k);
-        } else {
-          v = 0;
-          for (int b = 0; b < 4 && a + b < img_end; b++) v |= (uint32_t)a[b] << (8 * b);
-        }
-      }
-      dst[k] = v;
-    }
-    __syncwarp();
-    uint8_t* row = rowbuf[rr] + phase;
-    for (int k = g.valid + lane; k < OUT * 3 && k < g.valid + 4; k += 32) row[k] = 255;   // tail of the last word
-    if (lane < 3 && g.left) row[lane] = g.left[lane];
-    if (lane < 3 && g.right) row[(OUT - 1) * 3 + lane] = g.right[lane];
-    if (lane == 0) rowphase[rr] = phase;
-  }
-  __syncthreads();
-  const int X = tid;
-  if (o.batch_u8) {
-    for (int rr = 0; rr < 2 * kGatherPairs; rr++) {
-      uint8_t* dst = o.batch_u8 + (((int64_t)slot * OUT + 2 * jp0 + rr) * OUT) * 3;
-      const uint8_t* row = rowbuf[rr] + rowphase[rr];
-      for (int k = tid; k < OUT * 3; k += 128) dst[k] = row[k];
-    }
-  }
-  if (!o.batch) return;
-  if (o.layout == HIPAC_LAYOUT_S2D16_BF16) {
-    if (X >= OUT / 2) {
-      // threads 112..114 write the explicit zero columns 0, 1, 114 of the padded space-to-depth rows
-      if (X < OUT / 2 + 3) {
-        const int col = X - OUT / 2 < 2 ? X - OUT / 2 : HIPAC_S2D16_WIDTH - 1;
-        for (int q = 0; q < kGatherPairs; q++) {
-          uint4* dst = reinterpret_cast<uint4*>(o.batch + ((((int64_t)slot * (OUT / 2) + jp0 + q) * HIPAC_S2D16_WIDTH + col) << 4));
-          dst[0] = dst[1] = make_uint4(0u, 0u, 0u, 0u);
-        }
-      }
-      return;
-    }
-#pragma unroll 2
-    for (int q = 0; q < kGatherPairs; q++) {
-      const uint8_t* r0 = rowbuf[2 * q] + rowphase[2 * q] + 6 * X;        // 2 pixels x 3 channels of the even row
-      const uint8_t* r1 = rowbuf[2 * q + 1] + rowphase[2 * q + 1] + 6 * X;
-      uint32_t w[8];
-#pragma unroll
-      for (int k = 0; k < 3; k++) {
-        // s2d channel (dy*2+dx)*3+c = dy*6 + (dx*3+c): the 6 bytes of a row are already in channel order
-        w[k] = (uint32_t)lut[r0[2 * k] * 3 + (2 * k) % 3] | ((uint32_t)lut[r0[2 * k + 1] * 3 + (2 * k + 1) % 3] << 16);
-        w[3 + k] = (uint32_t)lut[r1[2 * k] * 3 + (2 * k) % 3] | ((uint32_t)lut[r1[2 * k + 1] * 3 + (2 * k + 1) % 3] << 16);
-      }
-      w[6] = w[7] = 0;
-      uint4* dst = reinterpret_cast<uint4*>(o.batch + ((((int64_t)slot * (OUT / 2) + jp0 + q) * HIPAC_S2D16_WIDTH + X + 2) << 4));
-      dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
-      dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
-    }
+  const int X = threadIdx.x;
+  const bool s2d = o.batch && o.layout == HIPAC_LAYOUT_S2D16_BF16;
+  // ---- per-patch constants: where output row j comes from ----
+  const uint8_t* base;          // interior source of output row 0, byte 0 = output column 0
+  int64_t stride;               // bytes between consecutive output rows
+  int nrows, valid;             // rows [0, nrows) exist in the source; bytes [0, valid) of a row exist
+  const uint8_t *top = nullptr, *bot = nullptr;       // rows 0 / 223 of the vertically clamped planes
+  bool has_right = false;
+  if (F1) {
+    base = p.rgb + (int64_t)y * p.pitch + (int64_t)x * 3, stride = p.pitch;
+    nrows = min(OUT, p.H - y), valid = min(OUT, p.W - x) * 3;
   } else {
-    for (int rr = 0; rr < 2 * kGatherPairs; rr++) {
-      uint16_t* dst = o.batch + (((int64_t)slot * OUT + 2 * jp0 + rr) * OUT) * 3;
-      const uint8_t* row = rowbuf[rr] + rowphase[rr];
-      for (int k = tid; k < OUT * 3; k += 128) dst[k] = lut[row[k] * 3 + k % 3];
+    const int J0 = y / G.f - G.Jbase, I0 = x / G.f, iyl = y / p.S - p.iy_begin;
+    const size_t ix = (size_t)(x / p.S);
+    base = G.plane[0][0] + ((size_t)J0 * G.Dw + I0) * 3, stride = (int64_t)G.Dw * 3;
+    nrows = min(OUT, G.Dh - J0), valid = max(0, min(OUT, G.Dw - I0)) * 3;
+    top = G.plane[1][0] + ((size_t)iyl * G.Dw + I0) * 3, bot = G.plane[2][0] + ((size_t)iyl * G.Dw + I0) * 3;
+    has_right = I0 + OUT - 1 < G.Dw;                     // else column 223 is white via `valid`
+    if (X < 4 * kGatherPairs) {                          // stage the ring pixels of this CTA's rows (clamp planes)
+      const int rr = X >> 1, side = X & 1, j = 2 * jp0 + rr;
+      uint32_t v = 0x00FFFFFFu;
+      if (j < nrows && (side == 0 || has_right)) {
+        const int vk = j == 0 ? 1 : (j == OUT - 1 ? 2 : 0);
+        const size_t row = vk == 0 ? (size_t)(J0 + j) : (size_t)iyl;
+        const uint8_t* q = G.plane[vk][1 + side] + (row * G.nx + ix) * 3;
+        v = q[0] | ((uint32_t)q[1] << 8) | ((uint32_t)q[2] << 16);
+      }
+      ring[rr][side] = v;
+    }
+    __syncthreads();
+  }
+  if (X >= OUT / 2) {
+    // threads 112..114 write the explicit zero columns 0, 1, 114 of the padded space-to-depth rows
+    if (s2d && X < OUT / 2 + 3) {
+      const int col = X - OUT / 2 < 2 ? X - OUT / 2 : HIPAC_S2D16_WIDTH - 1;
+      for (int q = 0; q < kGatherPairs; q++) {
+        const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+        st_global_256(o.batch + ((((int64_t)slot * (OUT / 2) + jp0 + q) * HIPAC_S2D16_WIDTH + col) << 4), z, z);
+      }
+    }
+    return;
+  }
+  // ---- per-thread constants ----
+  const int nv = valid - 6 * X;                 // valid bytes among this thread's 6; the rest is white padding
+  const uint32_t wm0 = nv >= 4 ? 0u : (nv <= 0 ? 0xFFFFFFFFu : 0xFFFFFFFFu << (8 * nv));
+  const uint32_t wm1 = nv >= 6 ? 0u : (nv <= 4 ? 0xFFFFu : 0xFF00u);
+  // ring merge: thread 0 replaces bytes 0..2 (column 0), thread 111 bytes 3..5 (column 223)
+  const bool ringL = !F1 && X == 0, ringR = !F1 && X == OUT / 2 - 1 && has_right;
+  const uint32_t keep0 = ringL ? 0xFF000000u : (ringR ? 0x00FFFFFFu : 0xFFFFFFFFu);
+  const uint32_t keep1 = ringR ? 0u : 0xFFFFu;
+  const uint32_t rsh = ringR ? 24 : 0;
+  const int rside = ringR ? 1 : 0;
+  const uint8_t* img_end = p.rgb + (int64_t)p.H * p.pitch;
+  // 6 bytes of one output row (columns 2X, 2X+1) as (bytes 0..3, bytes 4..5); `a` = address of byte 0
+  auto fetch = [&](const uint8_t* a, bool row_ok, int rr, uint32_t& e0, uint32_t& e1) {
+    const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(a) & 3) * 8;
+    const uint32_t* aw = reinterpret_cast<const uint32_t*>(a - (sh >> 3));
+    uint32_t w0, w1, w2;
+    if (!F1 || reinterpret_cast<const uint8_t*>(aw + 3) <= img_end) {
+      w0 = __ldg(aw), w1 = __ldg(aw + 1), w2 = __ldg(aw + 2);
+    } else {                                    // last bytes of the level image: never read past the buffer
+      uint32_t w[3] = {0, 0, 0};
+      for (int b = 0; b < 12; b++) {
+        const uint8_t* q = reinterpret_cast<const uint8_t*>(aw) + b;
+        if (q < img_end) w[b >> 2] |= (uint32_t)*q << (8 * (b & 3));
+      }
+      w0 = w[0], w1 = w[1], w2 = w[2];
+    }
+    e0 = __funnelshift_r(w0, w1, sh) | (row_ok ? wm0 : 0xFFFFFFFFu);
+    e1 = (__funnelshift_r(w1, w2, sh) & 0xFFFFu) | (row_ok ? wm1 : 0xFFFFu);
+    if (!F1) {
+      const uint32_t rv = ring[rr][rside];
+      e0 = (e0 & keep0) | ((rv << rsh) & ~keep0);
+      e1 = (e1 & keep1) | ((rv >> 8) & ~keep1 & 0xFFFFu);
+    }
+  };
+  const uint8_t* rowp = base + (int64_t)(2 * jp0) * stride + 6 * X;   // running pointer: row 2*(jp0+q)
+  const uint8_t* safe = base + 6 * X;                                  // any readable address for rows below the level
+#pragma unroll 2
+  for (int q = 0; q < kGatherPairs; q++, rowp += 2 * stride) {
+    const int j0 = 2 * (jp0 + q);
+    const bool okA = j0 < nrows, okB = j0 + 1 < nrows;
+    const uint8_t* pa = !okA ? safe : ((!F1 && j0 == 0) ? top + 6 * X : rowp);
+    const uint8_t* pb = !okB ? safe : ((!F1 && j0 + 1 == OUT - 1) ? bot + 6 * X : rowp + stride);
+    uint32_t e0, e1, f0, f1v;
+    fetch(pa, okA, 2 * q, e0, e1);
+    fetch(pb, okB, 2 * q + 1, f0, f1v);
+    if (o.batch_u8) {
+      uint16_t* d0 = reinterpret_cast<uint16_t*>(o.batch_u8 + (((int64_t)slot * OUT + j0) * OUT + 2 * X) * 3);
+      uint16_t* d1 = d0 + OUT * 3 / 2;
+      d0[0] = (uint16_t)e0, d0[1] = (uint16_t)(e0 >> 16), d0[2] = (uint16_t)e1;
+      d1[0] = (uint16_t)f0, d1[1] = (uint16_t)(f0 >> 16), d1[2] = (uint16_t)f1v;
+    }
+    if (!o.batch) continue;
+    // s2d channel (dy*2+dx)*3+c = dy*6 + (dx*3+c): the 6 bytes of a row are already in channel order R G B R G B
+    uint4 lo, hi;
+    lo.x = norm_pack(e0, 0, 0, 1, 1);
+    lo.y = norm_pack(e0, 2, 2, 3, 0);
+    lo.z = norm_pack(e1, 0, 1, 1, 2);
+    lo.w = norm_pack(f0, 0, 0, 1, 1);
+    hi.x = norm_pack(f0, 2, 2, 3, 0);
+    hi.y = norm_pack(f1v, 0, 1, 1, 2);
+    hi.z = hi.w = 0u;
+    if (s2d) {
+      st_global_256(o.batch + ((((int64_t)slot * (OUT / 2) + jp0 + q) * HIPAC_S2D16_WIDTH + X + 2) << 4), lo, hi);
+    } else {
+      uint32_t* d0 = reinterpret_cast<uint32_t*>(o.batch + (((int64_t)slot * OUT + j0) * OUT + 2 * X) * 3);
+      uint32_t* d1 = d0 + OUT * 3 / 2;
+      d0[0] = lo.x, d0[1] = lo.y, d0[2] = lo.z;
+      d1[0] = lo.w, d1[1] = hi.x, d1[2] = hi.y;
     }
   }
 }
@@ -673,7 +695,8 @@ static int fused_scan_impl(const ScanParams& p, const OutParams& o, uint8_t* fla
     }
     dim3 grid((unsigned)min(n_cand, capacity), OUT / 2 / kGatherPairs);
     ProfileScope ps("gather", stream, 0.0);
-    k_gather<<<grid, 128, 0, stream>>>(p, G, o, d_coords, d_count, capacity);
+    if (G.f == 1) k_gather<true><<<grid, 128, 0, stream>>>(p, G, o, d_coords, d_count, capacity);
+    else k_gather<false><<<grid, 128, 0, stream>>>(p, G, o, d_coords, d_count, capacity);
     count_launch(1);
   }
   HIPAC_CHECK_CUDA(cudaGetLastError());

@@ -21,16 +21,17 @@
 // Applicability (else the cp.async kernels of tile_scan_fused.cuh run): pitch % 16 == 0, 16-byte aligned image, and at
 // most kStreamMaxVar ring columns per strip.
 #pragma once
+#include <type_traits>
 
 constexpr int kStripUnits = 31;        // units per strip that produce outputs
 constexpr int kStreamRows = 8;         // image rows per pipeline stage
 constexpr int kStreamRowBytes = 800;   // staged row: 768 bytes + alignment phase + 64-bit over-read
 constexpr int kStreamMaxVar = 10;      // ring-variant columns per strip (3 channels each -> 30 lanes)
 #ifndef HIPAC_STREAM_STAGES
-#define HIPAC_STREAM_STAGES 3
+#define HIPAC_STREAM_STAGES 2
 #endif
 #ifndef HIPAC_STREAM_WARPS
-#define HIPAC_STREAM_WARPS 5
+#define HIPAC_STREAM_WARPS 8
 #endif
 constexpr int kStreamStages = HIPAC_STREAM_STAGES;
 constexpr int kStreamWarps = HIPAC_STREAM_WARPS;   // warps (independent items) per CTA
@@ -142,7 +143,7 @@ __global__ void __launch_bounds__(kStreamWarps * 32) k_scan_planes(ScanParams p,
   const int nstages = (nrows + kStreamRows - 1) / kStreamRows;
   const bool last_chunk = chunk == Z.n_chunks - 1;
   const int s_lo = max(Z.srow_lo, r_item);
-  const int s_hi = last_chunk ? Z.srow_hi : min(Z.srow_hi, F * Jb - HALF);
+  const int s_hi = max(s_lo, last_chunk ? Z.srow_hi : min(Z.srow_hi, F * Jb - HALF));
 
   // ---- columns of this strip ----
   const int u0 = strip * kStripUnits;               // first unit; unit u = pixels 8u - F/2 .. 8u - F/2 + 7
@@ -286,6 +287,9 @@ __global__ void __launch_bounds__(kStreamWarps * 32) k_scan_planes(ScanParams p,
       };
       const bool tA = is_top(J), tB = is_top(J - 1), bA = is_bot(J), bB = is_bot(J - 1);
       const bool var = tA || tB || bA || bB;
+      // the eight (F) rows of the block, instantiated with and without the ring-variant row accumulators
+      auto rows_of_block = [&](auto var_tag) {
+        constexpr bool VAR = decltype(var_tag)::value;
 #pragma unroll
       for (int m = 0; m < F; m++) {
         const int rr = b * F + m;
@@ -331,15 +335,16 @@ __global__ void __launch_bounds__(kStreamWarps * 32) k_scan_planes(ScanParams p,
           }
         }
         // ---- cell sums (rows of the image that this item owns) ----
-        if (r >= s_lo && r < s_hi) {
+        {
           uint32_t f = 0, g2 = 0;
 #pragma unroll
           for (int j = 0; j < 8; j++) {
             if (wFirst<F, OFF>(j)) f = __dp4a(w[j], wFirst<F, OFF>(j), f);
             if (wRest<F, OFF>(j)) g2 = __dp4a(w[j], wRest<F, OFF>(j), g2);
           }
-          acc_f += f - corr_f;
-          acc_r += g2 - corr_r;
+          const bool counted = (unsigned)(r - s_lo) < (unsigned)(s_hi - s_lo);   // branch-free: s_hi >= s_lo
+          acc_f += counted ? f - corr_f : 0u;
+          acc_r += counted ? g2 - corr_r : 0u;
         }
         // ---- ring-variant column (clamped 3F/2-tap window, 22-bit weights) ----
         h[3 * NB] = 0;
@@ -356,7 +361,7 @@ __global__ void __launch_bounds__(kStreamWarps * 32) k_scan_planes(ScanParams p,
           Uv[e] += (2 * m + 1) * h[e];
           Sv[e] += h[e];
         }
-        if (var) {
+        if constexpr (VAR) {
 #pragma unroll
           for (int e = 0; e < NH; e++) {
             if (tA && m >= HALF) Tt[e] += cs.left[m - HALF] * h[e];
@@ -380,6 +385,9 @@ __global__ void __launch_bounds__(kStreamWarps * 32) k_scan_planes(ScanParams p,
         }
         if (m == HALF - 1 && (F * J) % G.g == 0 && F * J > s_lo) flush_cells(F * J / G.g - 1);
       }
+      };
+      if (var) rows_of_block(std::true_type{});
+      else rows_of_block(std::false_type{});
       // ---- end of block J: D row J-1 = U(J-1) + V(J) ----
       if (q >= 1) {
         const size_t jr = (size_t)(J - 1 - G.Jbase);
