@@ -274,7 +274,9 @@ def run_ours(args):
                    "cache": "inputs (0.8 GB image + 0.27 GB mask per GPU) exceed the 126 MB L2; no flush needed",
                    "resnet_chunk": args.chunk, "e2e_upload_groups": args.groups},
         "e2e": {"value": round(total_surv_e / (ms_e2e * 1e-3), 1), "unit": "patches/s",
-                "h2d_bytes_per_step": int(img_h.numel() + msk_h.numel()),
+                "h2d_bytes_per_step": int(pipe.last_h2d_bytes),
+                "h2d_note": "image rows once + the non-zero 32-row blocks of the lesion mask (host block-max scan inside the "
+                            f"timed region); dense input is {int(img_h.numel() + msk_h.numel())} bytes",
                 "d2h_bytes_per_step": int(n_surv * (512 * 4 + 8 + 1) + 8), "ms_per_step": round(ms_e2e, 3)},
         "gpu_launches": launches,
         "clocks": clk.summary(),

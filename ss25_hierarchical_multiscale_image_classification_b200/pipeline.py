@@ -7,7 +7,9 @@ one pass: ``hipac_tile_scan`` writes the normalised bf16 batch that ``hipac_resn
 ``process_level``       inputs already in HBM.
 ``process_level_host``  inputs in (pinned) host memory: the upload is cut into row groups and overlapped
                         with the tile scan + ResNet18 of the previous group on a second stream, and the
-                        results come back into host buffers.
+                        results come back into host buffers.  The lesion mask is uploaded sparsely: the host
+                        finds its non-zero row blocks (one vectorised max per block, while the image DMA is in
+                        flight) and only those travel; the rest of the device mask stays zero.
 """
 from __future__ import annotations
 
@@ -68,15 +70,61 @@ def process_level(level_img: torch.Tensor, lesion_mask, level: int, packed: _fea
 class HostPipeline:
     """Reusable device/host staging buffers + copy stream for ``process_level_host``."""
 
+    MASK_BLOCK_ROWS = 32     # granularity of the sparse lesion-mask upload
+
     def __init__(self, height: int, width: int, device, with_mask: bool = True, capacity: int | None = None,
-                 num_classes: int = 2):
+                 num_classes: int = 2, sparse_mask: bool = True):
         self.device = torch.device(device)
         self.img = torch.empty((height, width, 3), dtype=torch.uint8, device=self.device)
-        self.mask = torch.empty((height, width), dtype=torch.uint8, device=self.device) if with_mask else None
+        # the device mask is kept all-zero outside the row blocks uploaded by the current step
+        self.mask = torch.zeros((height, width), dtype=torch.uint8, device=self.device) if with_mask else None
         self.copy_stream = torch.cuda.Stream(self.device)
         self.capacity = capacity
         self.num_classes = num_classes
+        self.sparse_mask = sparse_mask
+        self._dirty: list[tuple[int, int]] = []   # mask row ranges holding data of the previous step
+        self.last_h2d_bytes = 0
         self._host = None
+
+    def begin_step(self):
+        """Re-zero the mask rows the previous step uploaded (copy stream) and reset the byte counter."""
+        for r0, r1 in self._dirty:
+            self.mask[r0:r1].zero_()
+        self._dirty = []
+        self.last_h2d_bytes = 0
+
+    def upload_mask_rows(self, mask_host: torch.Tensor, r0: int, r1: int):
+        """Queue the upload of mask rows [r0, r1) on the current (copy) stream.  Sparse mode: one max per block of
+        MASK_BLOCK_ROWS rows on the host decides which blocks are non-zero; runs of such blocks are copied, the
+        others are already zero on the device."""
+        if r1 <= r0:
+            return
+        W = int(mask_host.shape[1])
+        if not self.sparse_mask or not mask_host.is_contiguous():
+            self.mask[r0:r1].copy_(mask_host[r0:r1], non_blocking=True)
+            self._dirty.append((r0, r1))
+            self.last_h2d_bytes += (r1 - r0) * W
+            return
+        R = self.MASK_BLOCK_ROWS
+        nfull = (r1 - r0) // R
+        flags = []
+        if nfull:
+            flags = mask_host[r0:r0 + nfull * R].view(nfull, R * W).amax(dim=1).ne(0).tolist()
+        if r0 + nfull * R < r1:
+            flags.append(bool(mask_host[r0 + nfull * R:r1].amax().item() != 0))
+        b, nb = 0, len(flags)
+        while b < nb:
+            if not flags[b]:
+                b += 1
+                continue
+            e = b
+            while e < nb and flags[e]:
+                e += 1
+            a0, a1 = r0 + b * R, min(r0 + e * R, r1)
+            self.mask[a0:a1].copy_(mask_host[a0:a1], non_blocking=True)
+            self._dirty.append((a0, a1))
+            self.last_h2d_bytes += (a1 - a0) * W
+            b = e
 
     def host_buffers(self, cap: int):
         if self._host is None or self._host[0].shape[0] < cap:
@@ -105,12 +153,15 @@ def process_level_host(level_img_host: torch.Tensor, mask_host, level: int, pack
     events, done_rows = [], i0 * S
     with torch.cuda.stream(pipe.copy_stream):
         pipe.copy_stream.wait_stream(main)          # previous step's kernels are done with the staging buffers
+        if pipe.mask is not None:
+            pipe.begin_step()
         for g in range(groups):
             need = min(H, (bounds[g + 1] - 1) * S + P + 8) if bounds[g + 1] > bounds[g] else done_rows
             if need > done_rows:
                 pipe.img[done_rows:need].copy_(level_img_host[done_rows:need], non_blocking=True)
+                pipe.last_h2d_bytes += (need - done_rows) * W * 3
                 if pipe.mask is not None and mask_host is not None:
-                    pipe.mask[done_rows:need].copy_(mask_host[done_rows:need], non_blocking=True)
+                    pipe.upload_mask_rows(mask_host, done_rows, need)   # host scan overlaps the image DMA just queued
                 done_rows = need
             ev = torch.cuda.Event()
             ev.record(pipe.copy_stream)

@@ -58,6 +58,33 @@ def test_pipelined_host_path_equals_resident_path(bench_image):
     assert torch.equal(host.coords[order], res.coords.cpu()) and torch.equal(host.labels[order], res.labels.cpu())
     assert torch.equal(host.features[order], res.features.cpu())          # identical kernels on identical inputs
     assert torch.equal(host.logits[order], res.logits.cpu())
+    dense = int(img_h.numel() + msk_h.numel())
+    assert int(img_h.numel()) < pipe.last_h2d_bytes < dense               # sparse mask upload: only non-zero row blocks
+
+
+def test_sparse_mask_upload_tracks_a_changing_mask():
+    """The device mask of a reused HostPipeline must equal the host mask of the CURRENT step (stale rows re-zeroed),
+    for ragged heights, dense masks and the dense-upload mode."""
+    from ss25_hierarchical_multiscale_image_classification_b200 import features, pipeline
+    rng = np.random.default_rng(3)
+    H, W = 1500, 2000                                                    # 1500 = 46 * 32 + 28: ragged last block
+    img = torch.from_numpy(rng.integers(0, 230, size=(H, W, 3), dtype=np.uint8)).pin_memory()
+    packed = features.pack_resnet18(orc.make_resnet18(seed=0, classifier=True).state_dict(), "cuda")
+    masks = []
+    for k, (r0, r1) in enumerate([(100, 140), (1480, 1500), (0, 1500), (700, 701)]):
+        m = np.zeros((H, W), np.uint8)
+        m[r0:r1, 50 + 10 * k: 900] = 1 + k
+        masks.append(torch.from_numpy(m).pin_memory())
+    for sparse in (True, False):
+        pipe = pipeline.HostPipeline(H, W, "cuda", with_mask=True, sparse_mask=sparse)
+        for m in masks + masks[:1]:
+            host = pipeline.process_level_host(img, m, 3, packed, pipe, groups=3)
+            assert torch.equal(pipe.mask.cpu(), m)
+            res = pipeline.process_level(img.cuda(), m.cuda(), 3, packed)
+            key = host.coords[:, 0].long() * (1 << 32) + host.coords[:, 1].long()
+            order = torch.argsort(key)
+            assert torch.equal(host.coords[order], res.coords.cpu()) and torch.equal(host.labels[order], res.labels.cpu())
+            assert 0 < int(res.labels.sum())
 
 
 def test_all_levels_pyramid_and_heatmap():
