@@ -120,6 +120,16 @@ int hipac_resnet18_forward(const void* d_packed, int num_classes,
                            float* d_feats, float* d_logits,
                            void* d_workspace, size_t workspace_bytes, int chunk, void* stream);
 
+/* Same forward with the patch count on the DEVICE: buffers, grids and tensor maps are sized for `capacity` patches and
+ * every kernel reads d_count[0] (e.g. the survivor counter written by hipac_tile_scan) when it starts, working on
+ * min(d_count[0], capacity) patches.  Nothing waits on the host, so tile scan + forward of one level image are enqueued
+ * back to back (and the sequence is CUDA-graph capturable); rows >= d_count[0] of d_feats / d_logits are left untouched.
+ * Workspace as for hipac_resnet18_workspace_bytes(capacity, chunk). */
+int hipac_resnet18_forward_dcount(const void* d_packed, int num_classes,
+                                  const void* d_batch, int layout, int capacity, const int32_t* d_count,
+                                  float* d_feats, float* d_logits,
+                                  void* d_workspace, size_t workspace_bytes, int chunk, void* stream);
+
 /* Test hook: one conv layer of the network on its own (layer index 0..19, network order), bf16 NHWC in/out
  * (layer 0 takes the S2D16 batch), optional residual.  Used by the per-layer parity tests. */
 int hipac_resnet18_conv_layer(const void* d_packed, int num_classes, int layer,

@@ -103,6 +103,8 @@ def _declare(l):
     l.hipac_resnet18_workspace_bytes.argtypes = [i32, i32]
     l.hipac_resnet18_forward.restype = i32
     l.hipac_resnet18_forward.argtypes = [vp, i32, vp, i32, i32, vp, vp, vp, sz, i32, vp]
+    l.hipac_resnet18_forward_dcount.restype = i32
+    l.hipac_resnet18_forward_dcount.argtypes = [vp, i32, vp, i32, i32, vp, vp, vp, vp, sz, i32, vp]
     l.hipac_resnet18_conv_ds_fused.restype = i32
     l.hipac_resnet18_conv_ds_fused.argtypes = [vp, i32, i32, vp, vp, vp, i32, vp]
     l.hipac_resnet18_stem.restype = i32
@@ -120,7 +122,7 @@ def _declare(l):
 EXPORTS = [
     "hipac_last_error", "hipac_abi_version", "hipac_launch_count", "hipac_tile_scan_workspace_bytes",
     "hipac_tile_scan", "hipac_tile_scan_set_count_buffer", "hipac_tile_scan_wait_count", "hipac_pillow_coeffs", "hipac_normalize_lut_bf16", "hipac_resnet18_packed_bytes",
-    "hipac_resnet18_pack", "hipac_resnet18_workspace_bytes", "hipac_resnet18_forward",
+    "hipac_resnet18_pack", "hipac_resnet18_workspace_bytes", "hipac_resnet18_forward", "hipac_resnet18_forward_dcount",
     "hipac_resnet18_conv_layer", "hipac_profile_enable", "hipac_profile_report", "hipac_debug_umma_shift", "hipac_resnet18_stem", "hipac_resnet18_conv_ds_fused",
 ]
 
@@ -145,9 +147,17 @@ def check(rc: int, what: str):
         raise RuntimeError(f"{what} failed ({rc}): {lib().hipac_last_error().decode()}")
 
 
+_profiling = threading.local()
+
+
 def profile(enable: bool):
     """Switch the library's per-kernel CUDA-event profiler on or off (calling thread)."""
     lib().hipac_profile_enable(int(enable))
+    _profiling.on = bool(enable)
+
+
+def profiling() -> bool:
+    return bool(getattr(_profiling, "on", False))
 
 
 def profile_report() -> dict:

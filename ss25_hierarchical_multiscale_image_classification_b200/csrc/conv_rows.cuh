@@ -21,6 +21,8 @@ struct RowConvParams {
   const float* bias;
   const __nv_bfloat16* residual;
   __nv_bfloat16* out;
+  const int* n_dev;  // device-count mode, see effective_patches()
+  int n_base;
 };
 
 template <int BN, int KC, int W, int R, bool RESIDENT>
@@ -72,6 +74,7 @@ k_conv3x3_rows(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const int num_tiles = effective_patches(p.n_dev, p.n_base, p.n_img) * (p.num_tiles / p.n_img);
 
   if (warp == 0) {
     // ===================== TMA producer (warp-uniform loop, one elected lane issues) =====================
@@ -83,7 +86,7 @@ k_conv3x3_rows(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       __syncwarp();
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int img = tile / TILES_PER_IMG, p0 = (tile - img * TILES_PER_IMG) * R;
         for (int kc = 0; kc < KC; kc++) {
           ptx::mbar_wait(&a_empty[sa], pa ^ 1);
@@ -114,7 +117,7 @@ k_conv3x3_rows(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0, acc = 0, acc_phase = 0;
       if (RESIDENT) ptx::mbar_wait(&b_full[0], 0);
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         ptx::mbar_wait(&tempty[acc], acc_phase ^ 1);
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
@@ -169,7 +172,7 @@ k_conv3x3_rows(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const bool valid = rr < R && x < W;
     const int grp = (warp - 2) >> 2;
     int it = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       if (epi_groups(BN) == 2 && (it & 1) != grp) continue;
       const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
       const int img = tile / TILES_PER_IMG, p0 = (tile - img * TILES_PER_IMG) * R;

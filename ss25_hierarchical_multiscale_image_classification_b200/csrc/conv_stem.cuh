@@ -25,6 +25,8 @@ struct StemParams {
   int num_blocks;  // n_img * (56 / kStemPB)
   const float* bias;
   __nv_bfloat16* out;  // [n][56][56][64]
+  const int* n_dev;    // device-count mode, see effective_patches()
+  int n_base;
 };
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
@@ -75,6 +77,7 @@ k_conv1_pool(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   constexpr int BLOCKS_PER_IMG = 56 / kStemPB;
+  const int num_blocks = effective_patches(p.n_dev, p.n_base, p.num_blocks / BLOCKS_PER_IMG) * BLOCKS_PER_IMG;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -85,7 +88,7 @@ k_conv1_pool(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     __syncwarp();
     int s = 0;
     uint32_t ph = 0;
-    for (int blk = blockIdx.x; blk < p.num_blocks; blk += gridDim.x) {
+    for (int blk = blockIdx.x; blk < num_blocks; blk += gridDim.x) {
       const int img = blk / BLOCKS_PER_IMG, py0 = (blk - img * BLOCKS_PER_IMG) * kStemPB;
       ptx::mbar_wait(&a_empty[s], ph ^ 1);
       if (ptx::elect_one()) {
@@ -102,7 +105,7 @@ k_conv1_pool(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     const uint64_t wdesc = ptx::make_smem_desc(ptx::smem_u32(sW), 128);
     int s = 0;
     uint32_t ph = 0, acc = 0, acc_phase = 0;
-    for (int blk = blockIdx.x; blk < p.num_blocks; blk += gridDim.x) {
+    for (int blk = blockIdx.x; blk < num_blocks; blk += gridDim.x) {
       const int py0 = (blk % BLOCKS_PER_IMG) * kStemPB;
       ptx::mbar_wait(&a_full[s], ph);
       ptx::tc_fence_after();
@@ -145,7 +148,7 @@ k_conv1_pool(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       bias[4 * i] = b.x, bias[4 * i + 1] = b.y, bias[4 * i + 2] = b.z, bias[4 * i + 3] = b.w;
     }
     __nv_bfloat162 vm[16];
-    for (int blk = blockIdx.x; blk < p.num_blocks; blk += gridDim.x) {
+    for (int blk = blockIdx.x; blk < num_blocks; blk += gridDim.x) {
       const int img = blk / BLOCKS_PER_IMG, py0 = (blk - img * BLOCKS_PER_IMG) * kStemPB;
       for (int t = (py0 == 0 ? 1 : 0); t <= 2 * kStemPB; t++) {
         const bool init = t == (py0 == 0 ? 1 : 0);    // first conv row of the block starts the running max

@@ -36,7 +36,19 @@ struct ConvParams {
   const float* bias;
   const __nv_bfloat16* residual;
   __nv_bfloat16* out;
+  const int* n_dev;  // device-side patch count (null: the host-side sizes above are exact)
+  int n_base;        // first patch of this chunk: the kernel works on clamp(*n_dev - n_base, 0, host n) patches
 };
+
+// Device-count mode: the host sizes grids, tensor maps and buffers for a CAPACITY; the number of patches that actually
+// exist is read from device memory when the kernel starts, so a whole step can be enqueued without a host round trip.
+__device__ __forceinline__ int effective_patches(const int* n_dev, int n_base, int n_cap) {
+  if (!n_dev) return n_cap;
+  const int n = __ldg(n_dev) - n_base;
+  return n < 0 ? 0 : (n < n_cap ? n : n_cap);
+}
+static thread_local const int* g_n_dev = nullptr;   // set by hipac_resnet18_forward_dcount around its launches
+static thread_local int g_n_base = 0;
 
 constexpr int kBM = 128;
 constexpr int kS2dW = HIPAC_S2D16_WIDTH;  // 112 + 3 explicit zero columns (2 left, 1 right)
@@ -149,7 +161,8 @@ k_conv_umma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+  const int M_total = effective_patches(p.n_dev, p.n_base, p.M_total / p.hw_out) * p.hw_out;
+  const int num_tiles = ((M_total + kBM - 1) / kBM) * p.num_n_tiles;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -225,7 +238,7 @@ k_conv_umma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
       const int m_tile = tile / p.num_n_tiles, n_tile = tile - m_tile * p.num_n_tiles;
       const int m = m_tile * kBM + row;
-      const bool valid = m < p.M_total;
+      const bool valid = m < M_total;
       {
         const size_t off = (size_t)m * p.cout + (size_t)n_tile * BN;
         epilogue_row<BN>(tmem_base + ((uint32_t)(wq * 32) << 16) + acc * BN, p.bias + n_tile * BN,
@@ -286,8 +299,10 @@ __global__ void __launch_bounds__(256) k_maxpool(const __nv_bfloat16* __restrict
 // Global average pool over 7x7 (fp32 accumulate) + optional Linear(512,k) in fp32. One CTA per patch.
 __global__ void __launch_bounds__(256) k_avgpool_fc(const __nv_bfloat16* __restrict__ in, float* __restrict__ feats,
                                                     float* __restrict__ logits, const float* __restrict__ fc_w,
-                                                    const float* __restrict__ fc_b, int num_classes) {
+                                                    const float* __restrict__ fc_b, int num_classes,
+                                                    const int* __restrict__ n_dev, int n_base) {
   const int img = blockIdx.x;
+  if (n_dev && img >= __ldg(n_dev) - n_base) return;
   __shared__ float f[512];
   const __nv_bfloat16* src = in + (int64_t)img * 49 * 512;
   for (int c2 = threadIdx.x; c2 < 256; c2 += 256) {
@@ -453,6 +468,7 @@ static int launch_rows_t(const uint8_t* d_packed, const PackedLayout& L, int lay
   if (int e = make_weight_map(&tmB, d_packed + L.w_off[layer], BN, 9 * KC * 64, BN)) return e;
   RowConvParams p;
   p.n_img = n, p.num_tiles = n * (W / R), p.relu = relu ? 1 : 0;
+  p.n_dev = g_n_dev, p.n_base = g_n_base;
   p.bias = reinterpret_cast<const float*>(d_packed + L.b_off[layer]);
   p.residual = reinterpret_cast<const __nv_bfloat16*>(residual);
   p.out = reinterpret_cast<__nv_bfloat16*>(out);
@@ -490,6 +506,7 @@ static int run_stem(const uint8_t* d_packed, const PackedLayout& L, const void* 
   if (int e = make_weight_map(&tmB, d_packed + L.w_off[0], 64, 256, 64)) return e;
   StemParams p;
   p.num_blocks = n * (56 / kStemPB);
+  p.n_dev = g_n_dev, p.n_base = g_n_base;
   p.bias = reinterpret_cast<const float*>(d_packed + L.b_off[0]);
   p.out = reinterpret_cast<__nv_bfloat16*>(out);
   const int grid = p.num_blocks < g_num_sms ? p.num_blocks : g_num_sms;
@@ -542,6 +559,7 @@ static int run_conv(const uint8_t* d_packed, const PackedLayout& L, int layer, c
   p.residual = reinterpret_cast<const __nv_bfloat16*>(residual);
   p.out = reinterpret_cast<__nv_bfloat16*>(out);
   p.num_m_tiles = (p.M_total + kBM - 1) / kBM;
+  p.n_dev = g_n_dev, p.n_base = g_n_base;
   p.num_kb2 = 0, p.stride2 = 1;
   const int bn = cs.cout >= 256 ? 256 : (cs.cout >= 128 ? 128 : 64);
   p.num_n_tiles = cs.cout / bn;
@@ -584,6 +602,7 @@ static int run_conv_ds_fused(const uint8_t* d_packed, const PackedLayout& L, int
   p.residual = nullptr;
   p.out = reinterpret_cast<__nv_bfloat16*>(out);
   p.num_m_tiles = (p.M_total + kBM - 1) / kBM;
+  p.n_dev = g_n_dev, p.n_base = g_n_base;
   const int bn = cs.cout >= 256 ? 256 : 128;
   p.num_n_tiles = cs.cout / bn;
   p.stride = 1, p.pad_w = p.pad_h = 1, p.kw = 3, p.kc_blocks = cs.cin / 64, p.num_kb = 9 * p.kc_blocks;
@@ -725,10 +744,14 @@ extern "C" int hipac_resnet18_stem(const void* d_packed, int num_classes, const 
   return run_stem(reinterpret_cast<const uint8_t*>(d_packed), L, d_in, d_out, n_patches, (cudaStream_t)stream_);
 }
 
-extern "C" int hipac_resnet18_forward(const void* d_packed, int num_classes, const void* d_batch, int layout, int n_patches,
-                                      float* d_feats, float* d_logits, void* d_workspace, size_t workspace_bytes, int chunk,
-                                      void* stream_) {
+static int forward_impl(const void* d_packed, int num_classes, const void* d_batch, int layout, int n_patches,
+                        float* d_feats, float* d_logits, void* d_workspace, size_t workspace_bytes, int chunk,
+                        void* stream_, const int* d_count) {
   cudaStream_t stream = (cudaStream_t)stream_;
+  struct CountScope {   // every launch below picks the device count up from these thread-locals
+    explicit CountScope(const int* c) { g_n_dev = c, g_n_base = 0; }
+    ~CountScope() { g_n_dev = nullptr, g_n_base = 0; }
+  } count_scope(d_count);
   HIPAC_REQUIRE(n_patches >= 0, "negative n_patches");
   if (n_patches == 0) return 0;
   HIPAC_REQUIRE(d_packed && d_batch && d_feats && d_workspace, "null pointer");
@@ -755,6 +778,7 @@ extern "C" int hipac_resnet18_forward(const void* d_packed, int num_classes, con
 
   for (int i0 = 0; i0 < n_patches; i0 += cmax) {
     const int n = n_patches - i0 < cmax ? n_patches - i0 : cmax;
+    g_n_base = i0;
     const void* x0;
     if (layout == HIPAC_LAYOUT_S2D16_BF16) {
       x0 = reinterpret_cast<const uint8_t*>(d_batch) + (size_t)i0 * kS2dBytes;
@@ -800,9 +824,24 @@ extern "C" int hipac_resnet18_forward(const void* d_packed, int num_classes, con
     k_avgpool_fc<<<n, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(A), d_feats + (size_t)i0 * 512,
                                         d_logits ? d_logits + (size_t)i0 * num_classes : nullptr,
                                         reinterpret_cast<const float*>(pk + L.fc_w_off),
-                                        reinterpret_cast<const float*>(pk + L.fc_b_off), num_classes);
+                                        reinterpret_cast<const float*>(pk + L.fc_b_off), num_classes, g_n_dev, g_n_base);
     count_launch(1);
   }
   HIPAC_CHECK_CUDA(cudaGetLastError());
   return 0;
+}
+
+extern "C" int hipac_resnet18_forward(const void* d_packed, int num_classes, const void* d_batch, int layout, int n_patches,
+                                      float* d_feats, float* d_logits, void* d_workspace, size_t workspace_bytes, int chunk,
+                                      void* stream) {
+  return forward_impl(d_packed, num_classes, d_batch, layout, n_patches, d_feats, d_logits, d_workspace, workspace_bytes, chunk,
+                      stream, nullptr);
+}
+
+extern "C" int hipac_resnet18_forward_dcount(const void* d_packed, int num_classes, const void* d_batch, int layout, int capacity,
+                                             const int32_t* d_count, float* d_feats, float* d_logits, void* d_workspace,
+                                             size_t workspace_bytes, int chunk, void* stream) {
+  HIPAC_REQUIRE(d_count != nullptr, "null device count");
+  return forward_impl(d_packed, num_classes, d_batch, layout, capacity, d_feats, d_logits, d_workspace, workspace_bytes, chunk,
+                      stream, d_count);
 }

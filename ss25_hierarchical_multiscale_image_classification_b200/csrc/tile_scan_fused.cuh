@@ -153,6 +153,43 @@ __global__ void __launch_bounds__(256) k_cell_stats(ScanParams p, FusedGeom G, i
   }
 }
 
+// pass A1': lesion votes only (the streaming pass already produced the byte sums).  The mask is almost everywhere
+// zero, so this is a pure stream: every thread ORs 16-byte chunks (4 independent loads in flight) and only a non-zero
+// chunk touches its cell (cells are multiples of 32 pixels wide, so an aligned 16-byte chunk never straddles two).
+__global__ void __launch_bounds__(256) k_cell_votes(ScanParams p, FusedGeom G, int row0, int nrows) {
+  const int cpr = (p.W + 15) >> 4;                       // 16-byte chunks per row (the last one may be partial)
+  const int64_t total = (int64_t)nrows * cpr;
+  const int64_t step = (int64_t)gridDim.x * 256;
+  for (int64_t i0 = (int64_t)blockIdx.x * 256 + threadIdx.x; i0 < total; i0 += 4 * step) {
+    uint4 v[4];
+    int rr[4], kk[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int64_t i = i0 + u * step;
+      v[u] = make_uint4(0, 0, 0, 0);
+      rr[u] = 0, kk[u] = 0;
+      if (i < total) {
+        rr[u] = (int)(i / cpr), kk[u] = (int)(i - (int64_t)rr[u] * cpr);
+        const uint8_t* src = p.mask + (int64_t)(row0 + rr[u]) * p.mask_pitch + kk[u] * 16;
+        if (kk[u] * 16 + 16 <= p.W) {
+          v[u] = ldg_nc_v4(src);
+        } else {                                          // ragged right edge: never read the pitch padding
+          uint32_t a = 0;
+          for (int b = 0; kk[u] * 16 + b < p.W; b++) a |= src[b];
+          v[u].x = a;
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      if (v[u].x | v[u].y | v[u].z | v[u].w) {
+        const int cyl = (row0 + rr[u]) / G.g - G.cy0, cx = kk[u] * 16 / G.g;
+        atomicOr(&G.cell_any[(size_t)cyl * G.ncx + cx], 1u);
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // per-candidate flags from the cell grid
 // ------------------------------------------------------------------------------------------
@@ -666,10 +703,17 @@ static int fused_scan_impl(const ScanParams& p, const OutParams& o, uint8_t* fla
     // one read of the image: cell sums + resampled planes; the lesion votes come from a mask-only pass
     if (int e = launch_scan_planes(p, G, stream)) return e;
   }
-  if (!stream_ok || p.mask) {
-    const int rows = min(p.H, (G.cy0 + G.ncy) * G.g) - G.cy0 * G.g;
-    dim3 grid(G.ncx, (rows + 31) / 32);
-    ProfileScope ps(stream_ok ? "cell_votes" : "cell_stats", stream, (double)rows * p.W * ((p.mask ? 1 : 0) + (stream_ok ? 0 : 3)));
+  const int cell_rows = min(p.H, (G.cy0 + G.ncy) * G.g) - G.cy0 * G.g;
+  if (stream_ok && p.mask && (p.mask_pitch & 15) == 0 && (reinterpret_cast<uintptr_t>(p.mask) & 15) == 0) {
+    const int64_t chunks = (int64_t)cell_rows * ((p.W + 15) >> 4);
+    const int64_t want = (chunks + 1023) / 1024;
+    const int grid = (int)(want < 148 * 16 ? want : 148 * 16);
+    ProfileScope ps("cell_votes", stream, (double)cell_rows * p.W);
+    k_cell_votes<<<grid, 256, 0, stream>>>(p, G, G.cy0 * G.g, cell_rows);
+    count_launch(1);
+  } else if (!stream_ok || p.mask) {
+    dim3 grid(G.ncx, (cell_rows + 31) / 32);
+    ProfileScope ps(stream_ok ? "cell_votes" : "cell_stats", stream, (double)cell_rows * p.W * ((p.mask ? 1 : 0) + (stream_ok ? 0 : 3)));
     k_cell_stats<<<grid, 256, 0, stream>>>(p, G, stream_ok ? 0 : 1);
     count_launch(1);
   }

@@ -68,7 +68,10 @@ def pack_resnet18(state_dict: dict, device, prefix: str = "", bn_eps: float = 1e
 _LAYOUT_BY_SHAPE = {(224, 224, 3): _lib.LAYOUT_NHWC3_BF16, (112, 115, 16): _lib.LAYOUT_S2D16_BF16}
 
 
-def _forward(batch: torch.Tensor, packed: PackedResNet18, want_logits: bool, chunk: int, stream=None):
+def _forward(batch: torch.Tensor, packed: PackedResNet18, want_logits: bool, chunk: int, stream=None,
+             count: torch.Tensor | None = None):
+    """``count``: int32 device tensor whose element 0 is the number of valid patches in ``batch`` (device-count mode:
+    ``batch.shape[0]`` is only the capacity; nothing here waits for the value)."""
     l = _lib.lib()
     if not (batch.is_cuda and batch.dtype == torch.bfloat16 and batch.dim() == 4 and tuple(batch.shape[1:]) in _LAYOUT_BY_SHAPE):
         raise ValueError("batch must be a CUDA bf16 tensor [N,224,224,3] or [N,112,115,16]")
@@ -87,23 +90,33 @@ def _forward(batch: torch.Tensor, packed: PackedResNet18, want_logits: bool, chu
             return feats, logits
         ws_bytes = l.hipac_resnet18_workspace_bytes(n, chunk)
         ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
-        rc = l.hipac_resnet18_forward(packed.blob.data_ptr(), packed.num_classes, batch.data_ptr(),
-                                      _LAYOUT_BY_SHAPE[tuple(batch.shape[1:])], n, feats.data_ptr(),
-                                      logits.data_ptr() if logits is not None else None, ws.data_ptr(), ws_bytes,
-                                      chunk, st.cuda_stream)
+        if count is None:
+            rc = l.hipac_resnet18_forward(packed.blob.data_ptr(), packed.num_classes, batch.data_ptr(),
+                                          _LAYOUT_BY_SHAPE[tuple(batch.shape[1:])], n, feats.data_ptr(),
+                                          logits.data_ptr() if logits is not None else None, ws.data_ptr(), ws_bytes,
+                                          chunk, st.cuda_stream)
+        else:
+            if not (count.is_cuda and count.dtype == torch.int32 and count.numel() >= 1):
+                raise ValueError("count must be a CUDA int32 tensor")
+            rc = l.hipac_resnet18_forward_dcount(packed.blob.data_ptr(), packed.num_classes, batch.data_ptr(),
+                                                 _LAYOUT_BY_SHAPE[tuple(batch.shape[1:])], n, count.data_ptr(),
+                                                 feats.data_ptr(), logits.data_ptr() if logits is not None else None,
+                                                 ws.data_ptr(), ws_bytes, chunk, st.cuda_stream)
         _lib.check(rc, "hipac_resnet18_forward")
         ws.record_stream(st)
     return feats, logits
 
 
-def extract_features_tensor(batch: torch.Tensor, packed: PackedResNet18, chunk: int = 4096, stream=None) -> torch.Tensor:
+def extract_features_tensor(batch: torch.Tensor, packed: PackedResNet18, chunk: int = 4096, stream=None,
+                            count: torch.Tensor | None = None) -> torch.Tensor:
     """float32 ``[N,512]`` pooled trunk features of a bf16 patch batch (asynchronous)."""
-    return _forward(batch, packed, False, chunk, stream)[0]
+    return _forward(batch, packed, False, chunk, stream, count)[0]
 
 
-def classify_tensor(batch: torch.Tensor, packed: PackedResNet18, chunk: int = 4096, stream=None):
+def classify_tensor(batch: torch.Tensor, packed: PackedResNet18, chunk: int = 4096, stream=None,
+                    count: torch.Tensor | None = None):
     """(features float32 ``[N,512]``, logits float32 ``[N,k]``) of a bf16 patch batch (asynchronous)."""
-    return _forward(batch, packed, True, chunk, stream)
+    return _forward(batch, packed, True, chunk, stream, count)
 
 
 def conv_layer(packed: PackedResNet18, layer: int, x: torch.Tensor, residual: torch.Tensor | None, relu: bool):

@@ -18,7 +18,8 @@ from dataclasses import dataclass
 import torch
 
 from . import features as _features
-from .preprocessing.tensor_api import extract_patches_tensor, grid_shape, patch_and_stride
+from . import _lib
+from .preprocessing.tensor_api import extract_patches_enqueue, extract_patches_tensor, grid_shape, patch_and_stride
 
 
 @dataclass
@@ -34,16 +35,29 @@ class LevelResult:
 
 
 def _process_rows(level_img, lesion_mask, level, packed, stride, rows, chunk, mode):
-    pb = extract_patches_tensor(level_img, lesion_mask, level, stride=stride, row_range=rows, layout="s2d16", mode=mode)
+    """Tile scan + ResNet18 of one candidate-row group, enqueued back to back: the network kernels take the survivor
+    count from device memory (``hipac_resnet18_forward_dcount``), so the host only learns it afterwards, to slice the
+    capacity-sized outputs -- while the GPU is already running the network."""
+    if _lib.profiling():
+        # the per-kernel profiler attributes flops by the host-side patch count: use the host-count path
+        pb = extract_patches_tensor(level_img, lesion_mask, level, stride=stride, row_range=rows, layout="s2d16", mode=mode)
+        if packed.num_classes > 0:
+            feats, logits = _features.classify_tensor(pb.batch, packed, chunk)
+        else:
+            feats, logits = _features.extract_features_tensor(pb.batch, packed, chunk), None
+        return LevelResult(pb.coords, pb.labels, feats, logits, pb.candidates)
+    pend = extract_patches_enqueue(level_img, lesion_mask, level, stride=stride, row_range=rows, layout="s2d16", mode=mode)
     if packed.num_classes > 0:
-        feats, logits = _features.classify_tensor(pb.batch, packed, chunk)
+        feats, logits = _features.classify_tensor(pend.batch, packed, chunk, count=pend.count)
     else:
-        feats, logits = _features.extract_features_tensor(pb.batch, packed, chunk), None
-    return LevelResult(pb.coords, pb.labels, feats, logits, pb.candidates)
+        feats, logits = _features.extract_features_tensor(pend.batch, packed, chunk, count=pend.count), None
+    pb = pend.resolve()
+    n = len(pb)
+    return LevelResult(pb.coords, pb.labels, feats[:n], logits[:n] if logits is not None else None, pb.candidates)
 
 
 def process_level(level_img: torch.Tensor, lesion_mask, level: int, packed: _features.PackedResNet18, stride=None,
-                  row_range=None, chunk: int = 4096, mode: str = "auto", max_candidates: int = 16384) -> LevelResult:
+                  row_range=None, chunk: int = 8192, mode: str = "auto", max_candidates: int = 16384) -> LevelResult:
     """Tile + tissue/lesion mask + ResNet18 features of a level image resident on the GPU.
 
     The batch buffer is sized for the worst case (every candidate survives), so levels with more than
@@ -136,7 +150,7 @@ class HostPipeline:
 
 
 def process_level_host(level_img_host: torch.Tensor, mask_host, level: int, packed: _features.PackedResNet18,
-                       pipe: HostPipeline, stride=None, row_range=None, groups: int = 4, chunk: int = 4096) -> LevelResult:
+                       pipe: HostPipeline, stride=None, row_range=None, groups: int = 4, chunk: int = 8192) -> LevelResult:
     """Same as ``process_level`` for HOST inputs; returns HOST tensors (pinned views, valid until the next call).
 
     The candidate grid rows are cut into ``groups`` contiguous groups.  All uploads are queued in row order

@@ -66,6 +66,34 @@ class PatchBatch:
         return int(self.coords.shape[0])
 
 
+@dataclass
+class PendingPatchBatch:
+    """A tile scan that has been enqueued but whose survivor count has not been read on the host yet: capacity-sized
+    tensors plus the device counter.  ``resolve()`` waits for the count only (not for the kernels) and slices."""
+    coords: torch.Tensor
+    labels: torch.Tensor
+    batch: torch.Tensor | None
+    images_u8: torch.Tensor | None
+    count: torch.Tensor             # int32 [2] on the device: {survivors, candidates}
+    capacity: int
+    layout: str | None
+    patch: int
+    stride: int
+    level: int
+
+    def resolve(self) -> "PatchBatch":
+        l = _lib.lib()
+        _lib.check(l.hipac_tile_scan_wait_count(), "hipac_tile_scan_wait_count")
+        h = _pinned_count()
+        n, n_c = int(h[0]), int(h[1])
+        if n > self.capacity:
+            raise RuntimeError(f"{n} survivors exceed capacity {self.capacity}; pass a smaller row_range or a larger capacity")
+        return PatchBatch(coords=self.coords[:n], labels=self.labels[:n],
+                          batch=self.batch[:n] if self.batch is not None else None,
+                          images_u8=self.images_u8[:n] if self.images_u8 is not None else None, layout=self.layout,
+                          candidates=n_c, patch=self.patch, stride=self.stride, level=self.level)
+
+
 def batch_shape(n: int, layout: str):
     return (n, OUT, OUT, 3) if layout == "nhwc3" else (n, OUT // 2, S2D16_WIDTH, 16)
 
@@ -74,14 +102,25 @@ def extract_patches_tensor(level_img: torch.Tensor, lesion_mask: torch.Tensor | 
                            stride=None, row_range=None, patch_size: int = 224, layout: str | None = "s2d16",
                            want_u8: bool = False, mode: str = "auto", capacity: int | None = None,
                            stream: torch.cuda.Stream | None = None, keep_all: bool = False) -> PatchBatch:
+    """``extract_patches_enqueue(...).resolve()``: see there."""
+    return extract_patches_enqueue(level_img, lesion_mask, level, stride=stride, row_range=row_range, patch_size=patch_size,
+                                   layout=layout, want_u8=want_u8, mode=mode, capacity=capacity, stream=stream,
+                                   keep_all=keep_all).resolve()
+
+
+def extract_patches_enqueue(level_img: torch.Tensor, lesion_mask: torch.Tensor | None, level: int,
+                            stride=None, row_range=None, patch_size: int = 224, layout: str | None = "s2d16",
+                            want_u8: bool = False, mode: str = "auto", capacity: int | None = None,
+                            stream: torch.cuda.Stream | None = None, keep_all: bool = False) -> PendingPatchBatch:
     """Tile one level image (uint8 ``[H,W,3]`` on a CUDA device) exactly as the reference does.
 
     ``lesion_mask``: uint8 ``[H,W]`` (>0 = lesion, the rasterised ``parse_xml_mask`` output,
     reference ``src/main.py:372-410``) or ``None`` -> every patch "normal" (``src/main.py:714-716``).
     ``row_range=(i0,i1)`` restricts to candidate grid rows ``y//stride in [i0,i1)`` -- the
     multi-GPU shard unit.  ``keep_all`` disables the tissue rejection (used on stacks of already
-    extracted patches).  Blocks only until the survivor count is known (after the compaction kernel); the
-    returned tensors are valid in stream order.
+    extracted patches).  Nothing blocks: the call returns capacity-sized tensors and the device-side survivor
+    counter; ``resolve()`` waits only until the count is known (after the compaction kernel) and slices, and
+    ``features.classify_tensor(..., count=pending.count)`` consumes the batch without any host round trip.
     """
     l = _lib.lib()
     if not (level_img.is_cuda and level_img.dtype == torch.uint8 and level_img.dim() == 3 and level_img.shape[2] == 3):
@@ -125,13 +164,7 @@ def extract_patches_tensor(level_img: torch.Tensor, lesion_mask: torch.Tensor | 
             batch.data_ptr() if batch is not None else None, _LAYOUTS[layout] if layout else 0,
             count.data_ptr(), cap, ws.data_ptr(), ws_bytes, m, st.cuda_stream)
         _lib.check(rc, "hipac_tile_scan")
-        # wait only for the compaction (count copied to pinned memory); the resample / gather kernels keep running and
-        # everything enqueued next on this stream is ordered behind them
-        _lib.check(l.hipac_tile_scan_wait_count(), "hipac_tile_scan_wait_count")
-        n, n_c = int(h_count[0]), int(h_count[1])
         ws.record_stream(st)
-    if n > cap:
-        raise RuntimeError(f"{n} survivors exceed capacity {cap}; pass a smaller row_range or a larger capacity")
-    return PatchBatch(coords=coords[:n], labels=labels[:n], batch=batch[:n] if batch is not None else None,
-                      images_u8=u8[:n] if u8 is not None else None, layout=layout, candidates=n_c, patch=P,
-                      stride=S, level=level)
+    del h_count   # registered with the library; read in resolve()
+    return PendingPatchBatch(coords=coords, labels=labels, batch=batch, images_u8=u8, count=count, capacity=cap,
+                             layout=layout, patch=P, stride=S, level=level)

@@ -176,3 +176,36 @@ def test_fused_projection_shortcut_vs_torch_fp32(net_and_packed, stage, n):
     scale = float(ref.abs().max())
     err = float((got - ref).abs().max())
     assert err <= 1.5 * 2.0 ** -8 * scale + 1e-3, f"stage {stage}: max err {err} at scale {scale}"
+
+
+@pytest.mark.parametrize("cap,n,chunk", [(11, 6, 4096), (11, 6, 4), (11, 11, 4096), (11, 0, 4096), (300, 150, 128), (5, 9, 4096)])
+def test_device_count_forward_equals_host_count(net_and_packed, cap, n, chunk):
+    """hipac_resnet18_forward_dcount (patch count read from device memory, everything sized for a capacity) gives the
+    same bits as the host-count call on the first min(count, capacity) patches and leaves the other rows untouched."""
+    from ss25_hierarchical_multiscale_image_classification_b200 import features
+    net, packed = net_and_packed
+    g = torch.Generator(device="cuda").manual_seed(cap * 1000 + n)
+    x = torch.randn((cap, 112, 115, 16), generator=g, device="cuda").to(torch.bfloat16)
+    x[:, :, :2] = 0
+    x[:, :, 114] = 0
+    x[..., 12:] = 0
+    m = min(n, cap)
+    count = torch.tensor([n, 12345], dtype=torch.int32, device="cuda")
+    f_ref, l_ref = features.classify_tensor(x[:m], packed, chunk) if m else (None, None)
+    f, l = features._forward(x, packed, True, chunk, count=count)
+    torch.cuda.synchronize()
+    if m:
+        assert torch.equal(f[:m], f_ref) and torch.equal(l[:m], l_ref)
+    # rows beyond the device count are never written
+    f2 = torch.full((cap, 512), 7.0, device="cuda")
+    lib = features._lib.lib()
+    ws_bytes = lib.hipac_resnet18_workspace_bytes(cap, chunk)
+    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device="cuda")
+    rc = lib.hipac_resnet18_forward_dcount(packed.blob.data_ptr(), packed.num_classes, x.data_ptr(), 2, cap, count.data_ptr(),
+                                           f2.data_ptr(), None, ws.data_ptr(), ws_bytes, chunk,
+                                           torch.cuda.current_stream().cuda_stream)
+    assert rc == 0
+    torch.cuda.synchronize()
+    assert bool((f2[m:] == 7.0).all())
+    if m:
+        assert torch.equal(f2[:m], f_ref)
