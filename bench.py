@@ -170,8 +170,14 @@ def run_ours(args):
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # torchrun exports OMP_NUM_THREADS=1; the e2e leg's host work (block-max scan of the lesion mask) wants this
+    # rank's share of the host cores
+    host_threads = max(1, min(16, len(os.sched_getaffinity(0)) // max(1, world)))
+    torch.set_num_threads(host_threads)
+    count_group = None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+        count_group = dist.new_group(backend="gloo")   # CPU-side exchange of the per-rank survivor counts
     ge.build()
     net = seeded_resnet18(seed=0, classifier=True)                        # random-init weights (BASELINE config)
     packed = features.pack_resnet18(net.state_dict(), dev)
@@ -188,7 +194,7 @@ def run_ours(args):
         coords = r.coords.to(dev).clone()
         coords[:, 1] += y0
         out = sharding.gather_survivors({"coords": coords, "labels": r.labels.to(dev), "features": r.features.to(dev),
-                                         "logits": r.logits.to(dev)}, sort=True)
+                                         "logits": r.logits.to(dev)}, sort=True, count_group=count_group)
         return int(out["coords"].shape[0])
 
     def step_resident():
@@ -272,7 +278,7 @@ def run_ours(args):
                    "sharding": f"tile-row ranges over {world} rank(s) of one {ROWS_PER_GPU * world}-row slide (content periodic in y, period "
                                f"{ROWS_PER_GPU}); NCCL all-gather of counts/coords/labels/features/logits + canonical sort",
                    "cache": "inputs (0.8 GB image + 0.27 GB mask per GPU) exceed the 126 MB L2; no flush needed",
-                   "resnet_chunk": args.chunk, "e2e_upload_groups": args.groups},
+                   "resnet_chunk": args.chunk, "e2e_upload_groups": args.groups, "host_threads_per_rank": host_threads},
         "e2e": {"value": round(total_surv_e / (ms_e2e * 1e-3), 1), "unit": "patches/s",
                 "h2d_bytes_per_step": int(pipe.last_h2d_bytes),
                 "h2d_note": "image rows once + the non-zero 32-row blocks of the lesion mask (host block-max scan inside the "

@@ -36,7 +36,7 @@ def canonical_order(coords: torch.Tensor) -> torch.Tensor:
     return torch.argsort(key, stable=True)
 
 
-def gather_survivors(tensors: dict, group=None, sort: bool = True) -> dict:
+def gather_survivors(tensors: dict, group=None, sort: bool = True, count_group=None) -> dict:
     """All-gather variable-length per-rank results.
 
     ``tensors`` maps names to tensors whose first dimension is this rank's survivor count (it must contain
@@ -45,17 +45,28 @@ def gather_survivors(tensors: dict, group=None, sort: bool = True) -> dict:
 
     One exchange step: the per-survivor rows of all tensors are packed side by side into one byte matrix, so the
     whole result travels in a single ``all_gather_into_tensor`` (after the tiny all-gather of the counts that
-    sizes the padding)."""
+    sizes the padding).
+
+    ``count_group``: an optional CPU-side (gloo) group over the same ranks.  Each rank already knows its own count
+    on the host (it sliced its tensors with it), so exchanging the counts over the CPU group keeps the GPU queue
+    free of host round trips: the data all-gather, the concatenation and the sort are then all enqueued
+    asynchronously and the next step's kernels can be queued behind them.  Without it the counts travel over
+    ``group`` and are read back, which drains the stream once per call."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     if world == 1:
         out = dict(tensors)
     else:
         ref = tensors["coords"]
         dev, n = ref.device, int(ref.shape[0])
-        cnt = torch.tensor([n], dtype=torch.int64, device=dev)
-        counts = torch.empty((world,), dtype=torch.int64, device=dev)
-        dist.all_gather_into_tensor(counts, cnt, group=group)
-        counts = counts.tolist()
+        if count_group is not None:
+            counts = torch.empty((world,), dtype=torch.int64)
+            dist.all_gather_into_tensor(counts, torch.tensor([n], dtype=torch.int64), group=count_group)
+            counts = counts.tolist()
+        else:
+            cnt = torch.tensor([n], dtype=torch.int64, device=dev)
+            counts = torch.empty((world,), dtype=torch.int64, device=dev)
+            dist.all_gather_into_tensor(counts, cnt, group=group)
+            counts = counts.tolist()
         mx = max(counts)
         # pack: each tensor contributes (row bytes rounded up to 8) columns of a uint8 matrix
         views, widths = [], []

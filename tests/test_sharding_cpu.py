@@ -73,7 +73,10 @@ def _worker(rank, world, port, level, w0, h0, seed, out_dir):
         assert np.array_equal(full["coords"], mine["coords"]) and np.array_equal(full["labels"], mine["labels"])
     coords = torch.from_numpy(mine["coords"])
     feats = coords.float().sum(1, keepdim=True).repeat(1, 4)             # stand-in payload tied to the coords
-    out = sharding.gather_survivors({"coords": coords, "labels": torch.from_numpy(mine["labels"]), "features": feats})
+    # odd ranks' worlds exchange the counts over a separate CPU group (the no-host-round-trip mode of the GPU bench)
+    cg = dist.new_group(backend="gloo") if world == 3 else None
+    out = sharding.gather_survivors({"coords": coords, "labels": torch.from_numpy(mine["labels"]), "features": feats},
+                                    count_group=cg)
     np.savez(os.path.join(out_dir, f"rank{rank}.npz"), coords=out["coords"].numpy(), labels=out["labels"].numpy(),
              features=out["features"].numpy())
     dist.destroy_process_group()
