@@ -177,6 +177,8 @@ def run_ours(args):
     count_group = None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+        if os.environ.get("MASTER_ADDR", "127.0.0.1") in ("127.0.0.1", "localhost"):
+            os.environ.setdefault("GLOO_SOCKET_IFNAME", "lo")   # single node: do not depend on the hostname resolving
         count_group = dist.new_group(backend="gloo")   # CPU-side exchange of the per-rank survivor counts
     ge.build()
     net = seeded_resnet18(seed=0, classifier=True)                        # random-init weights (BASELINE config)
@@ -401,7 +403,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--chunk", type=int, default=8192, help="patches per ResNet18 chunk")
     ap.add_argument("--cpu-candidates", type=int, default=96, help="candidates in the bounded CPU-baseline sample")
-    ap.add_argument("--groups", type=int, default=4, help="row groups of the pipelined host->device upload (e2e leg)")
+    ap.add_argument("--groups", type=int, default=6, help="row groups of the pipelined host->device upload (e2e leg)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     if args.impl == "reference":

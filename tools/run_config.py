@@ -83,6 +83,8 @@ def main():
     count_group = None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+        if os.environ.get("MASTER_ADDR", "127.0.0.1") in ("127.0.0.1", "localhost"):
+            os.environ.setdefault("GLOO_SOCKET_IFNAME", "lo")   # single node: do not depend on the hostname resolving
         count_group = dist.new_group(backend="gloo")
     eff_world, eff_rank = (world, rank) if world > 1 else (args.ranks or 1, args.rank)
     threads = max(1, min(16, len(os.sched_getaffinity(0)) // world))
