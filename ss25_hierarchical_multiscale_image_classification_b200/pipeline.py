@@ -151,6 +151,20 @@ class HostPipeline:
         return self._host
 
 
+def upload_group_bounds(i0: int, i1: int, groups: int):
+    """Candidate-row boundaries of the upload groups.  Tapered: the network of the LAST group cannot start before the
+    whole image has landed, so the last group is the exposed tail of the pipeline and gets the smallest share (the
+    taper is mild, largest / smallest = 2.5, so the first group does not delay the start of compute much)."""
+    groups = max(1, min(groups, i1 - i0))
+    w = [1.0 + 1.5 * (groups - 1 - g) / max(groups - 1, 1) for g in range(groups)]
+    acc, tot, bounds = 0.0, sum(w), [i0]
+    for g in range(groups):
+        acc += w[g]
+        bounds.append(max(bounds[-1], min(i1, i0 + int(round((i1 - i0) * acc / tot)))))
+    bounds[-1] = i1
+    return bounds
+
+
 def process_level_host(level_img_host: torch.Tensor, mask_host, level: int, packed: _features.PackedResNet18,
                        pipe: HostPipeline, stride=None, row_range=None, groups: int = 4, chunk: int = 8192) -> LevelResult:
     """Same as ``process_level`` for HOST inputs; returns HOST tensors (pinned views, valid until the next call).
@@ -162,16 +176,8 @@ def process_level_host(level_img_host: torch.Tensor, mask_host, level: int, pack
     P, S = patch_and_stride(level, stride)
     nx, ny_all = grid_shape(W, H, S)
     i0, i1 = (0, ny_all) if row_range is None else row_range
-    groups = max(1, min(groups, i1 - i0))
-    # Tapered groups: the network of the LAST group cannot start before the whole image has landed, so the last group is
-    # the exposed tail of the pipeline -- it gets the smallest share (weights groups, groups-1, ..., 1 would starve the
-    # first group instead: the taper is mild, largest/smallest = 2.5).
-    w = [1.0 + 1.5 * (groups - 1 - g) / max(groups - 1, 1) for g in range(groups)]
-    acc, tot, bounds = 0.0, sum(w), [i0]
-    for g in range(groups):
-        acc += w[g]
-        bounds.append(max(bounds[-1], min(i1, i0 + int(round((i1 - i0) * acc / tot)))))
-    bounds[-1] = i1
+    bounds = upload_group_bounds(i0, i1, groups)
+    groups = len(bounds) - 1
     dev = pipe.device
     main = torch.cuda.current_stream(dev)
     events, done_rows = [], i0 * S
