@@ -360,7 +360,8 @@ extern "C" size_t hipac_tile_scan_workspace_bytes(int H, int W, int P, int S, in
     p.H = H, p.W = W, p.P = P, p.S = S, p.nx = nx, p.ny = ny, p.iy_begin = iy_begin;
     b += fused_workspace_bytes_impl(p);
   }
-  return b + 256;
+  // tail pad: the gather kernel reads whole 32-bit words up to one patch row (224 * 3 bytes) past the end of a plane
+  return b + 1024;
 }
 
 extern "C" int hipac_tile_scan(const uint8_t* d_rgb, int H, int W, int64_t pitch_bytes, const uint8_t* d_mask,
