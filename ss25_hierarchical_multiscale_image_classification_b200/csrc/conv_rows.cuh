@@ -23,6 +23,7 @@ struct RowConvParams {
   __nv_bfloat16* out;
   const int* n_dev;  // device-count mode, see effective_patches()
   int n_base;
+  int reverse;       // tile order, see g_reverse
 };
 
 template <int BN, int KC, int W, int R, bool RESIDENT>
@@ -87,7 +88,8 @@ k_conv3x3_rows(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int img = tile / TILES_PER_IMG, p0 = (tile - img * TILES_PER_IMG) * R;
+        const int vt = p.reverse ? num_tiles - 1 - tile : tile;
+        const int img = vt / TILES_PER_IMG, p0 = (vt - img * TILES_PER_IMG) * R;
         for (int kc = 0; kc < KC; kc++) {
           ptx::mbar_wait(&a_empty[sa], pa ^ 1);
           if (ptx::elect_one()) {
@@ -175,7 +177,8 @@ k_conv3x3_rows(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       if (epi_groups(BN) == 2 && (it & 1) != grp) continue;
       const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
-      const int img = tile / TILES_PER_IMG, p0 = (tile - img * TILES_PER_IMG) * R;
+      const int vt = p.reverse ? num_tiles - 1 - tile : tile;
+      const int img = vt / TILES_PER_IMG, p0 = (vt - img * TILES_PER_IMG) * R;
       const size_t pix = ((size_t)img * H + p0 + rr) * W + x;
       epilogue_row<BN>(tmem_base + ((uint32_t)(wq * 32) << 16) + acc * BN, p.bias, p.residual ? p.residual + pix * BN : nullptr,
                        p.out + pix * BN, p.relu, valid, &tfull[acc], acc_phase);

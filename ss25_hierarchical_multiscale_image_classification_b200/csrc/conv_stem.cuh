@@ -27,6 +27,7 @@ struct StemParams {
   __nv_bfloat16* out;  // [n][56][56][64]
   const int* n_dev;    // device-count mode, see effective_patches()
   int n_base;
+  int reverse;         // block order, see g_reverse
 };
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
@@ -89,7 +90,8 @@ k_conv1_pool(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     int s = 0;
     uint32_t ph = 0;
     for (int blk = blockIdx.x; blk < num_blocks; blk += gridDim.x) {
-      const int img = blk / BLOCKS_PER_IMG, py0 = (blk - img * BLOCKS_PER_IMG) * kStemPB;
+      const int vb = p.reverse ? num_blocks - 1 - blk : blk;
+      const int img = vb / BLOCKS_PER_IMG, py0 = (vb - img * BLOCKS_PER_IMG) * kStemPB;
       ptx::mbar_wait(&a_empty[s], ph ^ 1);
       if (ptx::elect_one()) {
         ptx::mbar_arrive_expect_tx(&a_full[s], kStemRegionLoad);
@@ -106,7 +108,7 @@ k_conv1_pool(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     int s = 0;
     uint32_t ph = 0, acc = 0, acc_phase = 0;
     for (int blk = blockIdx.x; blk < num_blocks; blk += gridDim.x) {
-      const int py0 = (blk % BLOCKS_PER_IMG) * kStemPB;
+      const int py0 = ((p.reverse ? num_blocks - 1 - blk : blk) % BLOCKS_PER_IMG) * kStemPB;
       ptx::mbar_wait(&a_full[s], ph);
       ptx::tc_fence_after();
       const uint64_t rdesc = ptx::make_smem_desc(ptx::smem_u32(sA + s * kStemRegionBytes), 32);
@@ -149,7 +151,8 @@ k_conv1_pool(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     }
     __nv_bfloat162 vm[16];
     for (int blk = blockIdx.x; blk < num_blocks; blk += gridDim.x) {
-      const int img = blk / BLOCKS_PER_IMG, py0 = (blk - img * BLOCKS_PER_IMG) * kStemPB;
+      const int vb = p.reverse ? num_blocks - 1 - blk : blk;
+      const int img = vb / BLOCKS_PER_IMG, py0 = (vb - img * BLOCKS_PER_IMG) * kStemPB;
       for (int t = (py0 == 0 ? 1 : 0); t <= 2 * kStemPB; t++) {
         const bool init = t == (py0 == 0 ? 1 : 0);    // first conv row of the block starts the running max
         const bool closes = t > 0 && (t & 1) == 0;    // conv row 2*py + 1: pooled row py = py0 + t/2 - 1 is complete

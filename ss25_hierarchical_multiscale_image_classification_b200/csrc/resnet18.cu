@@ -38,6 +38,7 @@ struct ConvParams {
   __nv_bfloat16* out;
   const int* n_dev;  // device-side patch count (null: the host-side sizes above are exact)
   int n_base;        // first patch of this chunk: the kernel works on clamp(*n_dev - n_base, 0, host n) patches
+  int reverse;       // walk the tiles from the last to the first (see g_reverse)
 };
 
 // Device-count mode: the host sizes grids, tensor maps and buffers for a CAPACITY; the number of patches that actually
@@ -49,6 +50,10 @@ __device__ __forceinline__ int effective_patches(const int* n_dev, int n_base, i
 }
 static thread_local const int* g_n_dev = nullptr;   // set by hipac_resnet18_forward_dcount around its launches
 static thread_local int g_n_base = 0;
+// Boustrophedon tile order across the layers of one forward pass: a layer whose producer wrote images 0..n-1 walks
+// them n-1..0, so its first ~100 MB of reads are the producer's LAST writes and still sit in the 126 MB L2 (with the
+// same order on both sides they would be the oldest, long evicted).  Flipped after every launch of a forward pass.
+static thread_local int g_reverse = 0;
 
 constexpr int kBM = 128;
 constexpr int kS2dW = HIPAC_S2D16_WIDTH;  // 112 + 3 explicit zero columns (2 left, 1 right)
@@ -172,7 +177,8 @@ k_conv_umma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_tile = tile / p.num_n_tiles, n_tile = tile - m_tile * p.num_n_tiles;
+        const int vt = p.reverse ? num_tiles - 1 - tile : tile;
+        const int m_tile = vt / p.num_n_tiles, n_tile = vt - m_tile * p.num_n_tiles;
         const int m0 = m_tile * kBM;
         const int img = m0 / p.hw_out, rem = m0 - img * p.hw_out;
         const int p0 = rem / p.wout, q0 = rem - p0 * p.wout;
@@ -236,7 +242,8 @@ k_conv_umma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       if (epi_groups(BN) == 2 && (it & 1) != grp) continue;
       const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
-      const int m_tile = tile / p.num_n_tiles, n_tile = tile - m_tile * p.num_n_tiles;
+      const int vt = p.reverse ? num_tiles - 1 - tile : tile;
+      const int m_tile = vt / p.num_n_tiles, n_tile = vt - m_tile * p.num_n_tiles;
       const int m = m_tile * kBM + row;
       const bool valid = m < M_total;
       {
@@ -366,6 +373,7 @@ static bool g_fuse_downsample = true; // HIPAC_FUSE_DS=0 runs the 1x1 projection
 static bool g_use_row_kernels = true;  // HIPAC_CONV_ROWS=0 forces the im2col kernel everywhere (A/B comparison)
 
 // A/B switches for measurements; read once (the workspace size depends on them).
+static bool g_boustrophedon = true;   // alternate the tile order from layer to layer (A/B switch: HIPAC_BOUSTROPHEDON=0)
 static void read_env_flags() {
   static bool done = false;
   if (done) return;
@@ -373,6 +381,7 @@ static void read_env_flags() {
   if (const char* e = getenv("HIPAC_CONV_ROWS")) g_use_row_kernels = atoi(e) != 0;
   if (const char* e = getenv("HIPAC_FUSED_STEM")) g_use_fused_stem = atoi(e) != 0;
   if (const char* e = getenv("HIPAC_FUSE_DS")) g_fuse_downsample = atoi(e) != 0;
+  if (const char* e = getenv("HIPAC_BOUSTROPHEDON")) g_boustrophedon = atoi(e) != 0;
 }
 
 static int init_driver_api() {
@@ -468,7 +477,7 @@ static int launch_rows_t(const uint8_t* d_packed, const PackedLayout& L, int lay
   if (int e = make_weight_map(&tmB, d_packed + L.w_off[layer], BN, 9 * KC * 64, BN)) return e;
   RowConvParams p;
   p.n_img = n, p.num_tiles = n * (W / R), p.relu = relu ? 1 : 0;
-  p.n_dev = g_n_dev, p.n_base = g_n_base;
+  p.n_dev = g_n_dev, p.n_base = g_n_base, p.reverse = g_reverse;
   p.bias = reinterpret_cast<const float*>(d_packed + L.b_off[layer]);
   p.residual = reinterpret_cast<const __nv_bfloat16*>(residual);
   p.out = reinterpret_cast<__nv_bfloat16*>(out);
@@ -506,7 +515,7 @@ static int run_stem(const uint8_t* d_packed, const PackedLayout& L, const void* 
   if (int e = make_weight_map(&tmB, d_packed + L.w_off[0], 64, 256, 64)) return e;
   StemParams p;
   p.num_blocks = n * (56 / kStemPB);
-  p.n_dev = g_n_dev, p.n_base = g_n_base;
+  p.n_dev = g_n_dev, p.n_base = g_n_base, p.reverse = g_reverse;
   p.bias = reinterpret_cast<const float*>(d_packed + L.b_off[0]);
   p.out = reinterpret_cast<__nv_bfloat16*>(out);
   const int grid = p.num_blocks < g_num_sms ? p.num_blocks : g_num_sms;
@@ -559,7 +568,7 @@ static int run_conv(const uint8_t* d_packed, const PackedLayout& L, int layer, c
   p.residual = reinterpret_cast<const __nv_bfloat16*>(residual);
   p.out = reinterpret_cast<__nv_bfloat16*>(out);
   p.num_m_tiles = (p.M_total + kBM - 1) / kBM;
-  p.n_dev = g_n_dev, p.n_base = g_n_base;
+  p.n_dev = g_n_dev, p.n_base = g_n_base, p.reverse = g_reverse;
   p.num_kb2 = 0, p.stride2 = 1;
   const int bn = cs.cout >= 256 ? 256 : (cs.cout >= 128 ? 128 : 64);
   p.num_n_tiles = cs.cout / bn;
@@ -602,7 +611,7 @@ static int run_conv_ds_fused(const uint8_t* d_packed, const PackedLayout& L, int
   p.residual = nullptr;
   p.out = reinterpret_cast<__nv_bfloat16*>(out);
   p.num_m_tiles = (p.M_total + kBM - 1) / kBM;
-  p.n_dev = g_n_dev, p.n_base = g_n_base;
+  p.n_dev = g_n_dev, p.n_base = g_n_base, p.reverse = g_reverse;
   const int bn = cs.cout >= 256 ? 256 : 128;
   p.num_n_tiles = cs.cout / bn;
   p.stride = 1, p.pad_w = p.pad_h = 1, p.kw = 3, p.kc_blocks = cs.cin / 64, p.num_kb = 9 * p.kc_blocks;
@@ -749,8 +758,8 @@ static int forward_impl(const void* d_packed, int num_classes, const void* d_bat
                         void* stream_, const int* d_count) {
   cudaStream_t stream = (cudaStream_t)stream_;
   struct CountScope {   // every launch below picks the device count up from these thread-locals
-    explicit CountScope(const int* c) { g_n_dev = c, g_n_base = 0; }
-    ~CountScope() { g_n_dev = nullptr, g_n_base = 0; }
+    explicit CountScope(const int* c) { g_n_dev = c, g_n_base = 0, g_reverse = 0; }
+    ~CountScope() { g_n_dev = nullptr, g_n_base = 0, g_reverse = 0; }
   } count_scope(d_count);
   HIPAC_REQUIRE(n_patches >= 0, "negative n_patches");
   if (n_patches == 0) return 0;
@@ -791,11 +800,19 @@ static int forward_impl(const void* d_packed, int num_classes, const void* d_bat
       count_launch(1);
       x0 = s2d;
     }
+    // the batch was written in ascending patch order, so the first layer walks it descending, the next ascending, ...
+    int order = 1;
+    auto next_order = [&]() {
+      g_reverse = g_boustrophedon ? order : 0;
+      order ^= 1;
+    };
     auto conv = [&](int layer, const void* in, const void* res, void* out, bool relu) {
+      next_order();
       return run_conv(pk, L, layer, in, res, out, n, relu, stream);
     };
     int e = 0;
     if (g_use_fused_stem) {
+      next_order();
       if ((e = run_stem(pk, L, x0, A, n, stream))) return e;
     } else {
       if ((e = conv(0, x0, nullptr, c1, true))) return e;
@@ -813,6 +830,7 @@ static int forward_impl(const void* d_packed, int num_classes, const void* d_bat
       const int l0 = 5 + 5 * s;
       if ((e = conv(l0, A, nullptr, B, true))) return e;           // 3x3 / stride 2
       if (g_fuse_downsample) {
+        next_order();
         if ((e = run_conv_ds_fused(pk, L, s, B, A, C, n, stream))) return e;   // 3x3 + 1x1/s2 projection + ReLU, one accumulator
       } else {
         if ((e = conv(l0 + 2, A, nullptr, D, false))) return e;    // downsample 1x1 / stride 2 (+BN), no ReLU
