@@ -118,6 +118,27 @@ class ClockSampler:
                 "reasons": sorted(self.flags), "samples": len(self.sm), "source": self.source}
 
 
+def bind_near_gpu(index: int):
+    """Pin this process to the host cores NVML reports as local to GPU `index` (its NUMA node), BEFORE any pinned host
+    buffer is allocated: first-touch then places the staging memory next to the GPU's PCIe root, which is what the e2e
+    leg's H2D rate depends on when several ranks upload at once.  Best effort: returns the cpu count or None."""
+    try:
+        import pynvml as nv
+        nv.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = int(vis.split(",")[index]) if vis and all(v.strip().isdigit() for v in vis.split(",")) else index
+        h = nv.nvmlDeviceGetHandleByIndex(phys)
+        words = nv.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        near = {64 * i + b for i, w in enumerate(words) for b in range(64) if (w >> b) & 1}
+        allowed = near & os.sched_getaffinity(0)
+        if len(allowed) >= 2:
+            os.sched_setaffinity(0, allowed)
+            return len(allowed)
+    except Exception:
+        pass
+    return None
+
+
 def shard_rows(ny_total: int, world: int, rank: int):
     """Contiguous candidate tile-row range of `rank` (balanced by row count)."""
     base, rem = divmod(ny_total, world)
@@ -168,11 +189,14 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world != args.gpus:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run")
+    cpus_before = len(os.sched_getaffinity(0))
+    near_cpus = bind_near_gpu(local) if world > 1 else None
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     # torchrun exports OMP_NUM_THREADS=1; the e2e leg's host work (block-max scan of the lesion mask) wants this
     # rank's share of the host cores
-    host_threads = max(1, min(16, len(os.sched_getaffinity(0)) // max(1, world)))
+    ranks_sharing = max(1, round(world * len(os.sched_getaffinity(0)) / cpus_before))   # ranks bound to the same cores
+    host_threads = max(1, min(16, len(os.sched_getaffinity(0)) // ranks_sharing))
     torch.set_num_threads(host_threads)
     count_group = None
     if world > 1:
@@ -280,7 +304,7 @@ def run_ours(args):
                    "sharding": f"tile-row ranges over {world} rank(s) of one {ROWS_PER_GPU * world}-row slide (content periodic in y, period "
                                f"{ROWS_PER_GPU}); NCCL all-gather of counts/coords/labels/features/logits + canonical sort",
                    "cache": "inputs (0.8 GB image + 0.27 GB mask per GPU) exceed the 126 MB L2; no flush needed",
-                   "resnet_chunk": args.chunk, "e2e_upload_groups": args.groups, "host_threads_per_rank": host_threads},
+                   "resnet_chunk": args.chunk, "e2e_upload_groups": args.groups, "host_threads_per_rank": host_threads, "cpus_near_gpu": near_cpus},
         "e2e": {"value": round(total_surv_e / (ms_e2e * 1e-3), 1), "unit": "patches/s",
                 "h2d_bytes_per_step": int(pipe.last_h2d_bytes),
                 "h2d_note": "image rows once + the non-zero 32-row blocks of the lesion mask (host block-max scan inside the "
