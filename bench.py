@@ -398,6 +398,9 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    import torch
+    # torchrun exports OMP_NUM_THREADS=1: the reference arm gets every host core this process may use
+    torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
     vals, last, secs = [], None, []
     regions = cpu_sample_regions(args.cpu_candidates)
     for s in range(args.warmup + args.steps):
