@@ -528,11 +528,15 @@ __global__ void __launch_bounds__(128) k_gather(ScanParams p, FusedGeom G, OutPa
     }
     __syncthreads();
   }
-  if (X >= OUT / 2) {
-    // threads 112..114 write the explicit zero columns 0, 1, 114 of the padded space-to-depth rows
-    if (s2d && X < OUT / 2 + 3) {
-      const int col = X - OUT / 2 < 2 ? X - OUT / 2 : HIPAC_S2D16_WIDTH - 1;
-      for (int q = 0; q < kGatherPairs; q++) {
+  // thread -> (row-pair group g, column quad Xq): the thread owns output columns 4Xq .. 4Xq+3 (12 source bytes per row, two
+  // 32-byte space-to-depth pixels per row pair) of the row pairs g, g+2, g+4, g+6 of this CTA
+  const int g = X >> 6, Xq = X & 63;
+  constexpr int NQ = OUT / 4;                    // 56 column quads
+  if (Xq >= NQ) {
+    // threads 56..58 of each group write the explicit zero columns 0, 1, 114 of the padded space-to-depth rows
+    if (s2d && Xq < NQ + 3) {
+      const int col = Xq - NQ < 2 ? Xq - NQ : HIPAC_S2D16_WIDTH - 1;
+      for (int q = g; q < kGatherPairs; q += 2) {
         const uint4 z = make_uint4(0u, 0u, 0u, 0u);
         st_global_256(o.batch + ((((int64_t)slot * (OUT / 2) + jp0 + q) * HIPAC_S2D16_WIDTH + col) << 4), z, z);
       }
@@ -540,73 +544,78 @@ __global__ void __launch_bounds__(128) k_gather(ScanParams p, FusedGeom G, OutPa
     return;
   }
   // ---- per-thread constants ----
-  const int nv = valid - 6 * X;                 // valid bytes among this thread's 6; the rest is white padding
-  const uint32_t wm0 = nv >= 4 ? 0u : (nv <= 0 ? 0xFFFFFFFFu : 0xFFFFFFFFu << (8 * nv));
-  const uint32_t wm1 = nv >= 6 ? 0u : (nv <= 4 ? 0xFFFFu : 0xFF00u);
-  // ring merge: thread 0 replaces bytes 0..2 (column 0), thread 111 bytes 3..5 (column 223)
-  const bool ringL = !F1 && X == 0, ringR = !F1 && X == OUT / 2 - 1 && has_right;
-  const uint32_t keep0 = ringL ? 0xFF000000u : (ringR ? 0x00FFFFFFu : 0xFFFFFFFFu);
-  const uint32_t keep1 = ringR ? 0u : 0xFFFFu;
-  const uint32_t rsh = ringR ? 24 : 0;
-  const int rside = ringR ? 1 : 0;
+  const int nv = valid - 12 * Xq;               // valid bytes among this thread's 12; the rest is white padding
+  uint32_t wm[3];
+#pragma unroll
+  for (int k = 0; k < 3; k++) wm[k] = nv >= 4 * (k + 1) ? 0u : (nv <= 4 * k ? 0xFFFFFFFFu : 0xFFFFFFFFu << (8 * (nv - 4 * k)));
+  // ring merge: quad 0 replaces bytes 0..2 (column 0), quad 55 bytes 9..11 (column 223)
+  const bool ringL = !F1 && Xq == 0, ringR = !F1 && Xq == NQ - 1 && has_right;
   const uint8_t* img_end = p.rgb + (int64_t)p.H * p.pitch;
-  // 6 bytes of one output row (columns 2X, 2X+1) as (bytes 0..3, bytes 4..5); `a` = address of byte 0
-  auto fetch = [&](const uint8_t* a, bool row_ok, int rr, uint32_t& e0, uint32_t& e1) {
+  // 12 bytes of one output row (columns 4Xq .. 4Xq+3) as three words; `a` = address of byte 0
+  auto fetch = [&](const uint8_t* a, bool row_ok, int rr, uint32_t (&e)[3]) {
     const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(a) & 3) * 8;
     const uint32_t* aw = reinterpret_cast<const uint32_t*>(a - (sh >> 3));
-    uint32_t w0, w1, w2;
-    if (!F1 || reinterpret_cast<const uint8_t*>(aw + 3) <= img_end) {
-      w0 = __ldg(aw), w1 = __ldg(aw + 1), w2 = __ldg(aw + 2);
+    uint32_t w[4];
+    if (!F1 || reinterpret_cast<const uint8_t*>(aw + 4) <= img_end) {
+#pragma unroll
+      for (int k = 0; k < 4; k++) w[k] = __ldg(aw + k);
     } else {                                    // last bytes of the level image: never read past the buffer
-      uint32_t w[3] = {0, 0, 0};
-      for (int b = 0; b < 12; b++) {
+#pragma unroll
+      for (int k = 0; k < 4; k++) w[k] = 0;
+      for (int b = 0; b < 16; b++) {
         const uint8_t* q = reinterpret_cast<const uint8_t*>(aw) + b;
         if (q < img_end) w[b >> 2] |= (uint32_t)*q << (8 * (b & 3));
       }
-      w0 = w[0], w1 = w[1], w2 = w[2];
     }
-    e0 = __funnelshift_r(w0, w1, sh) | (row_ok ? wm0 : 0xFFFFFFFFu);
-    e1 = (__funnelshift_r(w1, w2, sh) & 0xFFFFu) | (row_ok ? wm1 : 0xFFFFu);
-    if (!F1) {
-      const uint32_t rv = ring[rr][rside];
-      e0 = (e0 & keep0) | ((rv << rsh) & ~keep0);
-      e1 = (e1 & keep1) | ((rv >> 8) & ~keep1 & 0xFFFFu);
-    }
+#pragma unroll
+    for (int k = 0; k < 3; k++) e[k] = __funnelshift_r(w[k], w[k + 1], sh) | (row_ok ? wm[k] : 0xFFFFFFFFu);
+    if (ringL) e[0] = (e[0] & 0xFF000000u) | ring[rr][0];
+    if (ringR) e[2] = (e[2] & 0x000000FFu) | (ring[rr][1] << 8);
   };
-  const uint8_t* rowp = base + (int64_t)(2 * jp0) * stride + 6 * X;   // running pointer: row 2*(jp0+q)
-  const uint8_t* safe = base + 6 * X;                                  // any readable address for rows below the level
+  const uint8_t* rowp = base + (int64_t)(2 * (jp0 + g)) * stride + 12 * Xq;   // running pointer: row 2*(jp0+q)
+  const uint8_t* safe = base + 12 * Xq;                                        // any readable address for rows below the level
 #pragma unroll 2
-  for (int q = 0; q < kGatherPairs; q++, rowp += 2 * stride) {
+  for (int q = g; q < kGatherPairs; q += 2, rowp += 4 * stride) {
     const int j0 = 2 * (jp0 + q);
     const bool okA = j0 < nrows, okB = j0 + 1 < nrows;
-    const uint8_t* pa = !okA ? safe : ((!F1 && j0 == 0) ? top + 6 * X : rowp);
-    const uint8_t* pb = !okB ? safe : ((!F1 && j0 + 1 == OUT - 1) ? bot + 6 * X : rowp + stride);
-    uint32_t e0, e1, f0, f1v;
-    fetch(pa, okA, 2 * q, e0, e1);
-    fetch(pb, okB, 2 * q + 1, f0, f1v);
+    const uint8_t* pa = !okA ? safe : ((!F1 && j0 == 0) ? top + 12 * Xq : rowp);
+    const uint8_t* pb = !okB ? safe : ((!F1 && j0 + 1 == OUT - 1) ? bot + 12 * Xq : rowp + stride);
+    uint32_t e[3], f[3];
+    fetch(pa, okA, 2 * q, e);
+    fetch(pb, okB, 2 * q + 1, f);
     if (o.batch_u8) {
-      uint16_t* d0 = reinterpret_cast<uint16_t*>(o.batch_u8 + (((int64_t)slot * OUT + j0) * OUT + 2 * X) * 3);
-      uint16_t* d1 = d0 + OUT * 3 / 2;
-      d0[0] = (uint16_t)e0, d0[1] = (uint16_t)(e0 >> 16), d0[2] = (uint16_t)e1;
-      d1[0] = (uint16_t)f0, d1[1] = (uint16_t)(f0 >> 16), d1[2] = (uint16_t)f1v;
+      uint32_t* d0 = reinterpret_cast<uint32_t*>(o.batch_u8 + (((int64_t)slot * OUT + j0) * OUT + 4 * Xq) * 3);
+      uint32_t* d1 = d0 + OUT * 3 / 4;
+      d0[0] = e[0], d0[1] = e[1], d0[2] = e[2];
+      d1[0] = f[0], d1[1] = f[1], d1[2] = f[2];
     }
     if (!o.batch) continue;
-    // s2d channel (dy*2+dx)*3+c = dy*6 + (dx*3+c): the 6 bytes of a row are already in channel order R G B R G B
-    uint4 lo, hi;
-    lo.x = norm_pack(e0, 0, 0, 1, 1);
-    lo.y = norm_pack(e0, 2, 2, 3, 0);
-    lo.z = norm_pack(e1, 0, 1, 1, 2);
-    lo.w = norm_pack(f0, 0, 0, 1, 1);
-    hi.x = norm_pack(f0, 2, 2, 3, 0);
-    hi.y = norm_pack(f1v, 0, 1, 1, 2);
-    hi.z = hi.w = 0u;
+    // s2d channel (dy*2+dx)*3+c = dy*6 + (dx*3+c): the 6 bytes a pixel pair takes from a row are already in channel
+    // order R G B R G B; bytes 0..5 of the 12 feed s2d pixel 2Xq, bytes 6..11 pixel 2Xq+1
+    uint4 lo0, hi0, lo1, hi1;
+    lo0.x = norm_pack(e[0], 0, 0, 1, 1);
+    lo0.y = norm_pack(e[0], 2, 2, 3, 0);
+    lo0.z = norm_pack(e[1], 0, 1, 1, 2);
+    lo0.w = norm_pack(f[0], 0, 0, 1, 1);
+    hi0.x = norm_pack(f[0], 2, 2, 3, 0);
+    hi0.y = norm_pack(f[1], 0, 1, 1, 2);
+    hi0.z = hi0.w = 0u;
+    lo1.x = norm_pack(e[1], 2, 0, 3, 1);
+    lo1.y = norm_pack(e[2], 0, 2, 1, 0);
+    lo1.z = norm_pack(e[2], 2, 1, 3, 2);
+    lo1.w = norm_pack(f[1], 2, 0, 3, 1);
+    hi1.x = norm_pack(f[2], 0, 2, 1, 0);
+    hi1.y = norm_pack(f[2], 2, 1, 3, 2);
+    hi1.z = hi1.w = 0u;
     if (s2d) {
-      st_global_256(o.batch + ((((int64_t)slot * (OUT / 2) + jp0 + q) * HIPAC_S2D16_WIDTH + X + 2) << 4), lo, hi);
+      uint16_t* dst = o.batch + ((((int64_t)slot * (OUT / 2) + jp0 + q) * HIPAC_S2D16_WIDTH + 2 * Xq + 2) << 4);
+      st_global_256(dst, lo0, hi0);
+      st_global_256(dst + 16, lo1, hi1);
     } else {
-      uint32_t* d0 = reinterpret_cast<uint32_t*>(o.batch + (((int64_t)slot * OUT + j0) * OUT + 2 * X) * 3);
+      uint32_t* d0 = reinterpret_cast<uint32_t*>(o.batch + (((int64_t)slot * OUT + j0) * OUT + 4 * Xq) * 3);
       uint32_t* d1 = d0 + OUT * 3 / 2;
-      d0[0] = lo.x, d0[1] = lo.y, d0[2] = lo.z;
-      d1[0] = lo.w, d1[1] = hi.x, d1[2] = hi.y;
+      d0[0] = lo0.x, d0[1] = lo0.y, d0[2] = lo0.z, d0[3] = lo1.x, d0[4] = lo1.y, d0[5] = lo1.z;
+      d1[0] = lo0.w, d1[1] = hi0.x, d1[2] = hi0.y, d1[3] = lo1.w, d1[4] = hi1.x, d1[5] = hi1.y;
     }
   }
 }
