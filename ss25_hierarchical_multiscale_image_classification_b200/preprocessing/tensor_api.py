@@ -80,12 +80,18 @@ class PendingPatchBatch:
     patch: int
     stride: int
     level: int
+    seq: int = 0                    # position in this thread's sequence of scans (the pinned count buffer is shared)
 
     def resolve(self) -> "PatchBatch":
         l = _lib.lib()
-        _lib.check(l.hipac_tile_scan_wait_count(), "hipac_tile_scan_wait_count")
-        h = _pinned_count()
-        n, n_c = int(h[0]), int(h[1])
+        if self.seq == getattr(_count_host, "seq", 0):
+            # fast path: this is the thread's most recent scan, its count is (or will be) in the pinned buffer
+            _lib.check(l.hipac_tile_scan_wait_count(), "hipac_tile_scan_wait_count")
+            h = _pinned_count()
+            n, n_c = int(h[0]), int(h[1])
+        else:
+            # a later scan has reused the pinned buffer: read this scan's own device counter (synchronises)
+            n, n_c = (int(v) for v in self.count.cpu().tolist())
         if n > self.capacity:
             raise RuntimeError(f"{n} survivors exceed capacity {self.capacity}; pass a smaller row_range or a larger capacity")
         return PatchBatch(coords=self.coords[:n], labels=self.labels[:n],
@@ -166,5 +172,6 @@ def extract_patches_enqueue(level_img: torch.Tensor, lesion_mask: torch.Tensor |
         _lib.check(rc, "hipac_tile_scan")
         ws.record_stream(st)
     del h_count   # registered with the library; read in resolve()
+    _count_host.seq = getattr(_count_host, "seq", 0) + 1
     return PendingPatchBatch(coords=coords, labels=labels, batch=batch, images_u8=u8, count=count, capacity=cap,
-                             layout=layout, patch=P, stride=S, level=level)
+                             layout=layout, patch=P, stride=S, level=level, seq=_count_host.seq)

@@ -193,3 +193,18 @@ def test_streaming_pass_row_range_shards():
     assert np.array_equal(coords[order], full.coords.cpu().numpy())
     assert np.array_equal(torch.cat([q.labels for q in parts]).cpu().numpy()[order], full.labels.cpu().numpy())
     assert np.array_equal(torch.cat([q.images_u8 for q in parts]).cpu().numpy()[order], full.images_u8.cpu().numpy())
+
+
+def test_pending_scans_resolve_in_any_order():
+    """Two scans enqueued back to back share the thread's pinned count buffer: resolving the OLDER one afterwards must
+    still return its own count (it falls back to its device counter)."""
+    from ss25_hierarchical_multiscale_image_classification_b200.preprocessing import extract_patches_enqueue, extract_patches_tensor
+    rng = np.random.default_rng(11)
+    a_img = torch.from_numpy(rng.integers(0, 200, size=(700, 900, 3), dtype=np.uint8)).cuda()       # all tissue
+    b_img = torch.from_numpy(np.full((500, 500, 3), 250, np.uint8)).cuda()                           # all background
+    pa = extract_patches_enqueue(a_img, None, 3, layout="nhwc3")
+    pb = extract_patches_enqueue(b_img, None, 3, layout="nhwc3")
+    rb, ra = pb.resolve(), pa.resolve()
+    assert len(rb) == 0 and rb.candidates == 9
+    want = extract_patches_tensor(a_img, None, 3, layout="nhwc3")
+    assert len(ra) == len(want) == 20 and ra.candidates == 20 and torch.equal(ra.coords, want.coords)
