@@ -312,7 +312,7 @@ def run_ours(args):
                 "d2h_bytes_per_step": int(n_surv * (512 * 4 + 8 + 1) + 8), "ms_per_step": round(ms_e2e, 3)},
         "gpu_launches": launches,
         "clocks": clk.summary(),
-        "roofline": {"bound": "tensor", "kernel": "k_conv_umma (all 20 conv layers)", "achieved": round(conv_tf, 1),
+        "roofline": {"bound": "tensor", "kernel": "conv stack: k_conv1_pool + k_conv3x3_rows + k_conv_umma (17 launches = 20 conv layers per step)", "achieved": round(conv_tf, 1),
                      "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
                      "frac": round(conv_tf / peaks["bf16_tflops_sustained"], 4),
                      "traffic": traffic.get("conv_dram_bytes_per_step"), "traffic_unit": "DRAM bytes per step over the 17 conv launches (ncu)",
