@@ -35,13 +35,23 @@ LEVEL, PATCH, STRIDE = 0, 1792, 224
 WIDTH, ROWS_PER_GPU = 16384, 16384
 SEED = 1234
 FLOP_PER_PATCH = 3.627e9          # SURVEY.md section 2.2 (conv 2*MAC + fc)
-S2D_BYTES = 112 * 112 * 16 * 2
+# algorithmic stage-1 output per survivor = the bf16 NHWC 224x224x3 image + coords (8) + label (1)
+ALGO_OUT_BYTES = 224 * 224 * 3 * 2 + 9
+# what the kernels really write per survivor: the S2D16 operand layout of conv1 (16 of 12 channels, 115 of 112 columns)
+S2D_BYTES = 112 * 115 * 16 * 2
+REF_STRIDE_MULT = 20              # --impl reference: the reference's own stride argument = 224 * this (every 20th grid column/row)
 
 
 def ncu_traffic():
-    """DRAM bytes per step from the committed ncu capture (profiles/r01_traffic.json), or {} if absent."""
+    """DRAM bytes per step from the newest committed ncu capture (profiles/r*_traffic.json), or {} if absent.  This is a
+    COMMITTED CONSTANT of the capture named in its "source" field, not measured in this run (ncu replays kernels ~40x, so it
+    cannot run inside the timed bench); `traffic_source` in the JSON line says so."""
     try:
-        return json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        pd = os.path.join(ROOT, "profiles")
+        names = sorted(f for f in os.listdir(pd) if f.endswith("_traffic.json"))
+        d = json.load(open(os.path.join(pd, names[-1])))
+        d["file"] = "profiles/" + names[-1]
+        return d
     except Exception:
         return {}
 
@@ -146,7 +156,7 @@ def shard_rows(ny_total: int, world: int, rank: int):
     return i0, i0 + base + (1 if rank < rem else 0)
 
 
-def build_slab(world: int, rank: int):
+def build_slab(world: int, rank: int, pinned: bool = True):
     """Pinned host tensors of this rank's row slab (+ halo) of the N x 16384-row synthetic slide.
 
     The slide's content repeats every 16384 rows (row y shows row y mod 16384 of the N = 1 slide), so the per-GPU
@@ -158,8 +168,10 @@ def build_slab(world: int, rank: int):
     ny_total = (H + STRIDE - 1) // STRIDE
     i0, i1 = shard_rows(ny_total, world, rank)
     y0, y1 = i0 * STRIDE, min(H, (i1 - 1) * STRIDE + PATCH)
-    img = torch.empty((y1 - y0, WIDTH, 3), dtype=torch.uint8).pin_memory()
-    msk = torch.empty((y1 - y0, WIDTH), dtype=torch.uint8).pin_memory()
+    img = torch.empty((y1 - y0, WIDTH, 3), dtype=torch.uint8)
+    msk = torch.empty((y1 - y0, WIDTH), dtype=torch.uint8)
+    if pinned:
+        img, msk = img.pin_memory(), msk.pin_memory()
     inp, mnp = img.numpy(), msk.numpy()
 
     def fill(r):
@@ -213,14 +225,18 @@ def run_ours(args):
     n_cand = ((WIDTH + STRIDE - 1) // STRIDE) * (i1 - i0)
     pipe = pipeline.HostPipeline(int(img_h.shape[0]), WIDTH, dev, with_mask=True, num_classes=2)
 
+    last_gathered = {}
+
     def gather(r):
         """The path's one exchange step: all-gather of counts / coords / labels / features / logits."""
         if world == 1:
+            last_gathered["out"] = {"coords": r.coords, "labels": r.labels, "features": r.features, "logits": r.logits}
             return len(r)
         coords = r.coords.to(dev).clone()
         coords[:, 1] += y0
         out = sharding.gather_survivors({"coords": coords, "labels": r.labels.to(dev), "features": r.features.to(dev),
                                          "logits": r.logits.to(dev)}, sort=True, count_group=count_group)
+        last_gathered["out"] = out
         return int(out["coords"].shape[0])
 
     def step_resident():
@@ -259,6 +275,13 @@ def run_ours(args):
     with ClockSampler(local) as clk:
         ms_step, total_surv, pb = timed(step_resident, args.steps, args.warmup)
     launches = int(_lib.lib().hipac_launch_count(1)) // (args.steps + args.warmup)
+    # the gathered, canonically sorted patch set of the last resident step (every rank holds the same one)
+    res = {k: v.cpu().numpy() for k, v in last_gathered["out"].items()}
+    order = np.lexsort((res["coords"][:, 1], res["coords"][:, 0]))
+    import zlib
+    crc = 0
+    for k in ("coords", "labels", "features", "logits"):
+        crc = zlib.crc32(np.ascontiguousarray(res[k][order]).tobytes(), crc)
     ms_e2e, total_surv_e, _ = timed(step_e2e, max(2, args.steps // 2), 1)
     n_surv = len(pb)
 
@@ -277,7 +300,9 @@ def run_ours(args):
     conv_tf = conv_flops / (conv_ms * 1e-3) / 1e12 if conv_ms else 0.0
     s1 = {k: v for k, v in prof.items() if not k.startswith(("conv", "maxpool", "avgpool", "pack"))}
     s1_ms = sum(v["ms"] for v in s1.values()) / 2
-    s1_bytes = img_d.numel() + msk_d.numel() + n_surv * (S2D_BYTES + 9)
+    s1_bytes = img_d.numel() + msk_d.numel() + n_surv * ALGO_OUT_BYTES
+    s1_written = n_surv * (S2D_BYTES + 9)                                        # what the kernels really write
+    s1_gbs = s1_bytes / (s1_ms * 1e-3) / 1e9 if s1_ms else 0.0
     kernels = {k: {"launches_per_step": v["launches"] // 2, "ms_per_step": round(v["ms"] / 2, 4),
                    **({"tflops": round(v["work"] / (v["ms"] * 1e-3) / 1e12, 1)} if k.startswith("conv") and v["ms"] else {})}
                for k, v in prof.items()}
@@ -286,7 +311,24 @@ def run_ours(args):
         if world > 1:
             dist.destroy_process_group()
         return
-    cpu = cpu_baseline_sample(step=0, budget_candidates=args.cpu_candidates) if world == 1 and not args.no_cpu else None
+    cpu, parity = None, None
+    if world == 1 and not args.no_cpu:
+        port_rec, port = cpu_port_sample(args.cpu_candidates)
+        parity = parity_block(res, port)
+        if reference_available():
+            torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
+            step = reference_as_written_step(png=True)
+            cpu = reference_record(step, int(torch.get_num_threads()))
+            # the reference's own decisions on its sub-lattice vs the GPU arm's survivors at the same grid points
+            stride = STRIDE * REF_STRIDE_MULT
+            ours = {f"tumor_900_x{x}_y{y}_{'tumor' if l else 'normal'}.png" for (x, y), l in zip(res["coords"].tolist(), res["labels"].tolist())
+                    if x % stride == 0 and y % stride == 0}
+            parity["reference_as_written"] = {"n_candidates": step["candidates"], "n_survivors": step["survivors"],
+                                              "file_names_equal": bool(ours == set(step["names"]))}
+            parity["pass"] = bool(parity["pass"] and ours == set(step["names"]))
+            cpu["port"] = port_rec
+        else:
+            cpu = port_rec
     out = {
         "metric": "patches/sec (tile+mask+ResNet18 features)",
         "value": round(total_surv / (ms_step * 1e-3), 1),
@@ -312,20 +354,33 @@ def run_ours(args):
                 "d2h_bytes_per_step": int(n_surv * (512 * 4 + 8 + 1) + 8), "ms_per_step": round(ms_e2e, 3)},
         "gpu_launches": launches,
         "clocks": clk.summary(),
-        "roofline": {"bound": "tensor", "kernel": "conv stack: k_conv1_pool + k_conv3x3_rows + k_conv_umma (17 launches = 20 conv layers per step)", "achieved": round(conv_tf, 1),
-                     "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                     "frac": round(conv_tf / peaks["bf16_tflops_sustained"], 4),
-                     "traffic": traffic.get("conv_dram_bytes_per_step"), "traffic_unit": "DRAM bytes per step over the 17 conv launches (ncu)",
+        "patch_set_crc32": f"{crc:08x}",
+        "roofline": {"bound": "tensor", "kernel": f"conv stack: k_conv1_pool + k_conv3x3_rows + k_conv_umma ({sum(v['launches'] for v in conv.values()) // 2} launches = 20 conv layers per step)",
+                     "achieved": round(conv_tf, 1),
+                     "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+                     "frac": round(conv_tf / peaks["bf16_tflops"], 4),
+                     "peak_note": "burst cuBLAS bf16 figure (the timed region is a fraction of a second); against the sustained "
+                                  f"figure {peaks['bf16_tflops_sustained']} the fraction is {round(conv_tf / peaks['bf16_tflops_sustained'], 4)}",
+                     "traffic": traffic.get("conv_dram_bytes_per_step"), "traffic_unit": "DRAM bytes per step over the conv launches",
+                     "traffic_source": f"committed ncu capture {traffic.get('file')} ({traffic.get('source')}), not measured in this run",
                      "algorithmic_flops_per_step": conv_flops / 2, "peak_source": peak_src,
                      "conv_ms_per_step": round(conv_ms / 2, 3)},
         "roofline_stage1": {"bound": "hbm", "kernel": "stage-1 tile scan (all kernels)",
-                            "achieved": round(s1_bytes / (s1_ms * 1e-3) / 1e9, 1) if s1_ms else None,
+                            "achieved": round(s1_gbs, 1) if s1_ms else None,
                             "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                            "frac": round(s1_bytes / (s1_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], 4) if s1_ms else None,
+                            "frac": round(s1_gbs / peaks["hbm_gbs"], 4) if s1_ms else None,
+                            "frac_of_nominal_8TBs": round(s1_gbs / 8000.0, 4) if s1_ms else None,
                             "ms_per_step": round(s1_ms, 3), "algorithmic_bytes": int(s1_bytes),
-                            "traffic": traffic.get("stage1_dram_bytes_per_step")},
+                            "algorithmic_bytes_note": "3HW image + HW mask + survivors x (224*224*3*2 + 9) (SURVEY.md 8d)",
+                            "written_bytes": int(s1_written),
+                            "written_note": "the batch is stored in conv1's S2D16 operand layout (16 of 12 channels, 115 of 112 columns): "
+                                            f"{round(s1_written / max(n_surv * ALGO_OUT_BYTES, 1), 3)}x the algorithmic output bytes",
+                            "traffic": traffic.get("stage1_dram_bytes_per_step"),
+                            "traffic_source": f"committed ncu capture {traffic.get('file')} ({traffic.get('source')}), not measured in this run"},
         "kernels": kernels,
     }
+    if parity:
+        out["parity"] = parity
     if cpu:
         out["cpu_baseline"] = cpu
     print(json.dumps(out), flush=True)
@@ -355,20 +410,19 @@ def cpu_sample_regions(budget_candidates: int):
     return sample, cache, k
 
 
-def cpu_baseline_sample(step: int, budget_candidates: int, regions=None):
-    """Time the CPU port of the reference path on an every-k-th-candidate sample of the N=1 workload."""
+def cpu_port_sample(budget_candidates: int, regions=None):
+    """The CPU PORT of the reference path (oracle/cpu_pipeline.py style) on an every-k-th-candidate sample of the N=1
+    workload: timing record + everything the parity block needs (decisions, labels, fp32 features and logits)."""
     import torch
     from oracle import cpu_pipeline, hipac_oracle as orc
 
-    H = ROWS_PER_GPU
     sample, cache, k = regions or cpu_sample_regions(budget_candidates)
     net = orc.make_resnet18(seed=0, classifier=True)
 
     from PIL import Image
     t0 = time.perf_counter()
-    patches, n_c = [], 0
+    patches, kept, labels, decisions = [], [], [], {}
     for (x, y) in sample:                                      # the reference's per-candidate body (src/main.py:688-727)
-        n_c += 1
         rgb, m = cache[(x, y)]
         region = Image.fromarray(np.dstack([rgb, np.full(rgb.shape[:2], 255, np.uint8)]), "RGBA").convert("RGB")
         if region.size != (PATCH, PATCH):
@@ -376,49 +430,155 @@ def cpu_baseline_sample(step: int, budget_candidates: int, regions=None):
             padded.paste(region, (0, 0))
             region = padded
         mask_patch = Image.fromarray(m, "L").crop((0, 0, PATCH, PATCH))
-        _label = 1 if np.any(np.array(mask_patch) > 0) else 0
-        if np.mean(np.array(region)) > 240:
+        label = 1 if np.any(np.array(mask_patch) > 0) else 0
+        keep = not (np.mean(np.array(region)) > 240)
+        decisions[(x, y)] = (keep, label)
+        if not keep:
             continue
         patches.append(region)
+        kept.append((x, y))
+        labels.append(label)
     t1 = time.perf_counter()
     feats = cpu_pipeline.stage2_reference_loop(patches, net, batch=64)
     t2 = time.perf_counter()
+    with torch.no_grad():
+        logits = net.fc(torch.from_numpy(feats)).numpy() if len(feats) else np.zeros((0, 2), np.float32)
     total = t2 - t0
-    return {"value": round(len(patches) / total, 2), "unit": "patches/s", "cores": int(torch.get_num_threads()),
-            "kind": "port",
-            "sample": f"every {k}-th candidate of the N=1 workload: {n_c} candidates -> {len(patches)} survivors; "
-                      f"stage 1 (single thread, as the reference; no PNG write) {t1 - t0:.2f} s, stage 2 (Resize+ToTensor+"
-                      f"Normalize per patch, fp32 ResNet18 on {torch.get_num_threads()} threads, batch 64) {t2 - t1:.2f} s",
-            "candidates_per_s": round(n_c / total, 2), "host_cpus": os.cpu_count(),
-            "feature_checksum": float(np.abs(feats).sum())}
+    rec = {"value": round(len(patches) / total, 2), "unit": "patches/s", "cores": int(torch.get_num_threads()),
+           "kind": "port",
+           "sample": f"every {k}-th candidate of the N=1 workload: {len(sample)} candidates -> {len(patches)} survivors; "
+                     f"stage 1 (single thread, as the reference; no PNG write) {t1 - t0:.2f} s, stage 2 (Resize+ToTensor+"
+                     f"Normalize per patch, fp32 ResNet18 on {torch.get_num_threads()} threads, batch 64) {t2 - t1:.2f} s",
+           "candidates_per_s": round(len(sample) / total, 2), "host_cpus": os.cpu_count(),
+           "feature_checksum": float(np.abs(feats).sum())}
+    return rec, {"decisions": decisions, "kept": kept, "labels": labels, "features": feats, "logits": logits}
+
+
+def parity_block(gpu, port):
+    """GPU arm vs the CPU oracle port on the sampled candidates of the FULL-SIZE workload: keep/reject decisions, labels
+    (bit-exact bar), features (cosine >= 0.9995, max|d|/max|ref| <= 1e-2) and classifier argmax (>= 99.9 %)."""
+    gx = {(int(x), int(y)): i for i, (x, y) in enumerate(gpu["coords"].tolist())}
+    dec = port["decisions"]
+    coords_equal = all(((xy in gx) == keep) for xy, (keep, _) in dec.items())
+    labels_equal = all(int(gpu["labels"][gx[xy]]) == lab for xy, (keep, lab) in dec.items() if keep and xy in gx)
+    idx = [gx[xy] for xy in port["kept"] if xy in gx]
+    ok = len(idx) == len(port["kept"]) and len(idx) > 0
+    out = {"against": "oracle port (fp32 torch, same seeded weights) on the cpu_baseline sample of the full-size workload",
+           "n_candidates": len(dec), "n": len(idx), "coords_equal": bool(coords_equal), "labels_equal": bool(labels_equal)}
+    if ok:
+        g, r = gpu["features"][idx].astype(np.float64), port["features"].astype(np.float64)
+        cos = (g * r).sum(1) / (np.linalg.norm(g, axis=1) * np.linalg.norm(r, axis=1))
+        maxrel = np.abs(g - r).max(1) / np.abs(r).max(1)
+        gl, rl = gpu["logits"][idx], port["logits"]
+        out.update({"min_cos": round(float(cos.min()), 7), "max_rel": float(f"{maxrel.max():.3e}"),
+                    "argmax_agree": round(float((gl.argmax(1) == rl.argmax(1)).mean()), 6),
+                    "min_logit_margin_fp32": round(float(np.abs(rl[:, 0] - rl[:, 1]).min()), 5),
+                    "max_logit_diff_error": float(f"{np.abs((gl[:, 1] - gl[:, 0]) - (rl[:, 1] - rl[:, 0])).max():.3e}")})
+        out["pass"] = bool(coords_equal and labels_equal and cos.min() >= 0.9995 and maxrel.max() <= 1e-2 and out["argmax_agree"] >= 0.999)
+    else:
+        out["pass"] = False
+    return out
+
+
+# ---- the reference AS WRITTEN (oracle/ref_harness.py drives the unmodified src/main.py from baseline/_ref) -------------
+_ref_slide = None
+
+
+def reference_slide():
+    """The N=1 bench slide as an OpenSlide duck type for the reference's own code (level 0 only) + its lesion mask."""
+    global _ref_slide
+    if _ref_slide is None:
+        from ss25_hierarchical_multiscale_image_classification_b200.synthetic import SyntheticSlide
+        img, msk, _ = build_slab(1, 0, pinned=False)
+        _ref_slide = (SyntheticSlide(levels=[img.numpy()], name="tumor_900"), msk.numpy())
+        from oracle import ref_harness as rh
+        rh.load_reference_main()                            # importing the reference's module is not a timed step either
+    return _ref_slide
+
+
+def reference_available():
+    from oracle import ref_harness as rh
+    return rh.reference_available()
+
+
+def reference_as_written_step(png: bool = True):
+    """One bounded step of the reference as written: ``extract_patches(level=0, stride=224*REF_STRIDE_MULT)`` -- the
+    reference's own stride argument, i.e. every REF_STRIDE_MULT-th column and row of the workload's 224-px candidate
+    grid over the WHOLE 16384^2 slide (16 full-size 1792^2 candidates) -- then ``extract_features(level=0)`` reading the
+    PNGs back through ``PatchDataset`` + ``DataLoader(batch_size=512, num_workers=8)`` (src/main.py:805-894).
+    ``png=False``: ``Image.save`` captured in memory (pure-compute stage 1) and the feature loop replayed in process."""
+    import torch
+    from oracle import ref_harness as rh
+    slide, mask = reference_slide()
+    stride = STRIDE * REF_STRIDE_MULT
+    n_cand = len(range(0, WIDTH, stride)) * len(range(0, ROWS_PER_GPU, stride))
+    if png:
+        r = rh.run_reference_as_written(slide, LEVEL, stride=stride, mask_arr=mask)
+        surv, s1, s2, names = int(r["n_png"]), r["stage1_s"], r["stage2_s"], r["paths"]
+        checksum = float(np.abs(r["features"]).sum())
+    else:
+        t0 = time.perf_counter()
+        saved = rh.run_reference_extract_patches(slide, LEVEL, stride=stride, mask_arr=mask)
+        t1 = time.perf_counter()
+        torch.manual_seed(0)
+        feats = rh.run_reference_features([r[4] for r in saved], None, batch=512)
+        t2 = time.perf_counter()
+        surv, s1, s2, names, checksum = len(saved), t1 - t0, t2 - t1, [r[0] for r in saved], float(np.abs(feats).sum())
+    return {"candidates": n_cand, "survivors": surv, "stage1_s": s1, "stage2_s": s2, "names": names, "feature_checksum": checksum}
+
+
+def reference_record(step, cores):
+    tot = step["stage1_s"] + step["stage2_s"]
+    return {"value": round(step["survivors"] / tot, 3), "unit": "patches/s", "cores": cores, "kind": "reference",
+            "sample": f"the unmodified reference (baseline/_ref/src/main.py) on the N=1 slide with its own stride argument = "
+                      f"{STRIDE * REF_STRIDE_MULT} (every {REF_STRIDE_MULT}-th column and row of the 224-px grid): {step['candidates']} "
+                      f"candidates -> {step['survivors']} survivors; extract_patches incl. PNG write {step['stage1_s']:.2f} s (single "
+                      f"thread, as written), extract_features incl. PNG decode + Resize via DataLoader(num_workers=8) {step['stage2_s']:.2f} s",
+            "candidates_per_s": round(step["candidates"] / tot, 3), "host_cpus": os.cpu_count(),
+            "feature_checksum": step["feature_checksum"]}
 
 
 def run_reference(args):
-    """`--impl reference`: the CPU port of the reference path on host cores, bounded sample per step."""
+    """`--impl reference`: the reference's own CPU implementation of the path on the box's host cores, each step a bounded
+    sample (see reference_as_written_step).  Falls back to the oracle port only if baseline/_ref is absent."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import torch
     # torchrun exports OMP_NUM_THREADS=1: the reference arm gets every host core this process may use
-    torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
-    vals, last, secs = [], None, []
-    regions = cpu_sample_regions(args.cpu_candidates)
+    cores = max(1, len(os.sched_getaffinity(0)))
+    torch.set_num_threads(cores)
+    as_written = reference_available()
+    vals, secs, last, extra = [], [], None, {}
+    regions = None if as_written else cpu_sample_regions(args.cpu_candidates)
+    if as_written:
+        reference_slide()                                   # synthetic-data generation is not reference work
     for s in range(args.warmup + args.steps):
         t0 = time.perf_counter()
-        r = cpu_baseline_sample(step=s, budget_candidates=args.cpu_candidates, regions=regions)
+        if as_written:
+            rec = reference_record(reference_as_written_step(png=True), cores)
+        else:
+            rec, _ = cpu_port_sample(args.cpu_candidates, regions)
         if s >= args.warmup:
-            vals.append(r)
+            vals.append(rec)
             secs.append(time.perf_counter() - t0)
-        last = r
+        last = rec
+    if as_written:
+        nopng = reference_as_written_step(png=False)
+        extra = {"no_png_value": round(nopng["survivors"] / (nopng["stage1_s"] + nopng["stage2_s"]), 3),
+                 "no_png_note": f"same sample with Image.save captured in memory and the feature loop replayed in process (no "
+                                f"DataLoader workers): stage 1 {nopng['stage1_s']:.2f} s, stage 2 {nopng['stage2_s']:.2f} s"}
     tot_surv = sum(float(v["value"]) for v in vals) / len(vals)
-    out = {"impl": "reference", "metric": "patches/sec (tile+mask+ResNet18 features)", "value": round(tot_surv, 2),
+    out = {"impl": "reference", "metric": "patches/sec (tile+mask+ResNet18 features)", "value": round(tot_surv, 3),
            "unit": "patches/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": round(1e3 * sum(secs) / len(secs), 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-           "dtype": "u8 + fp32 (CPU)", "data": "synthetic (same slide and weights as the GPU arm)",
-           "config": {"workload": "configs[1] (bounded every-k-th-candidate sample per step), CPU port of the reference path",
+           "dtype": "u8 + fp32 (CPU)", "data": "synthetic (same slide as the GPU arm; random-init ResNet18 as the reference builds it)",
+           "config": {"workload": "configs[1] (bounded sample per step: the reference's extract_patches + extract_features as written, "
+                                  f"stride argument {STRIDE * REF_STRIDE_MULT})" if as_written else
+                                  "configs[1] (bounded every-k-th-candidate sample per step), CPU port of the reference path",
                       "level": LEVEL, "patch": PATCH, "stride": STRIDE, "width": WIDTH, "rows_per_gpu": ROWS_PER_GPU},
-           "cpu_baseline": {**last, "value": round(tot_surv, 2)},
-           "e2e": {"value": round(tot_surv, 2), "unit": "patches/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+           "cpu_baseline": {**last, "value": round(tot_surv, 3), **extra},
+           "e2e": {"value": round(tot_surv, 3), "unit": "patches/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out), flush=True)
 
 

@@ -27,7 +27,22 @@ import types
 
 import numpy as np
 
-REF_ROOT = os.environ.get("HIPAC_REFERENCE_ROOT", "/root/reference")
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _find_reference_root() -> str:
+    """``HIPAC_REFERENCE_ROOT``, else the read-only checkout of the dev container, else the git-ignored copy of the few
+    needed files that ``oracle/fetch_reference.py`` leaves under ``baseline/_ref`` (that one travels to the GPU box)."""
+    env = os.environ.get("HIPAC_REFERENCE_ROOT")
+    if env:
+        return env
+    for cand in ("/root/reference", os.path.join(_REPO, "baseline", "_ref")):
+        if os.path.isfile(os.path.join(cand, "src", "main.py")):
+            return cand
+    return "/root/reference"
+
+
+REF_ROOT = _find_reference_root()
 
 
 def reference_available() -> bool:
@@ -88,7 +103,7 @@ def load_reference_main():
 
 
 def run_reference_extract_patches(slide, level: int, stride=None, with_mask: bool = True,
-                                  keep_images: bool = True):
+                                  keep_images: bool = True, mask_arr=None):
     """Call the reference's ``extract_patches(level=..., stride=...)`` on one synthetic slide.
 
     Returns a list of ``(name, x, y, label, rgb uint8[P,P,3] | None)`` in the order the
@@ -109,7 +124,8 @@ def run_reference_extract_patches(slide, level: int, stride=None, with_mask: boo
         x = int(parts[-3][1:])
         saved.append((base, x, y, label, np.array(self) if keep_images else None))
 
-    mask_arr = slide.lesion_mask(level) if with_mask else None
+    if mask_arr is None:
+        mask_arr = slide.lesion_mask(level) if with_mask else None
 
     def fake_parse_xml_mask(xml_path, level_dims, sl):
         assert tuple(level_dims) == tuple(sl.level_dimensions[level])
@@ -138,6 +154,95 @@ def run_reference_extract_patches(slide, level: int, stride=None, with_mask: boo
             os.chdir(cwd)
             _slides.pop(name, None)
     return saved
+
+
+class _OfflineResNet18Classifier:
+    """Stand-in for the reference's ``ResNet18Classifier`` INSIDE ``extract_features`` only: the real constructor calls
+    ``models.resnet18(pretrained=True)`` (src/models/resnet.py:63-65), i.e. downloads ImageNet weights, which cannot
+    work offline.  The object is never run by ``extract_features`` and none of its weights reach the feature model (the
+    key filter at src/main.py:852-859 matches nothing), so an identically shaped random-init module
+    is an exact substitute for this call site."""
+
+    def __new__(cls):
+        import torch
+        import torchvision
+
+        class M(torch.nn.Module):
+            def __init__(self):
+                super().__init__()
+                self.model = torchvision.models.resnet18(weights=None)
+                self.model.fc = torch.nn.Linear(512, 2)
+
+            def forward(self, x):
+                return self.model(x)
+
+        return M()
+
+
+def run_reference_as_written(slide, level: int, stride=None, with_mask: bool = True, seed: int = 0, mask_arr=None):
+    """The reference's two stages EXACTLY as its CLI runs them, coupled through PNG files on disk:
+    ``extract_patches(level=, stride=)`` (src/main.py:609-732, real ``Image.save``) and then
+    ``extract_features(level=)`` (src/main.py:805-894: ``PatchDataset`` + ``DataLoader(batch_size=512, num_workers=8)``
+    + ``ResNet18FeatureExtractor`` + ``np.save``), in a temporary working directory.
+
+    Only substitutions: the openslide / lxml / matplotlib / skimage import stubs, ``parse_xml_mask`` returning the
+    synthetic mask, and ``ResNet18Classifier`` -> ``_OfflineResNet18Classifier`` (see there).  ``torch.manual_seed(seed)``
+    is set before ``extract_features`` so its random-init feature model is reproducible.
+
+    Returns dict(stage1_s, stage2_s, n_png, features f32[N,512], labels, paths)."""
+    import time
+
+    import torch
+    from PIL import Image
+
+    ref = load_reference_main()
+    name = slide.name
+    _slides[name] = slide
+    if mask_arr is None and with_mask:
+        mask_arr = slide.lesion_mask(level)
+
+    def fake_parse_xml_mask(xml_path, level_dims, sl):
+        return Image.fromarray(mask_arr, "L")
+
+    cwd = os.getcwd()
+    orig_parse, orig_cls = ref.parse_xml_mask, ref.ResNet18Classifier
+    out = {}
+    with tempfile.TemporaryDirectory() as tmp:
+        img_dir = os.path.join(tmp, "data", "camelyon16", "train", "img")
+        ann_dir = os.path.join(tmp, "data", "camelyon16", "train", "mask", "annotations")
+        os.makedirs(img_dir)
+        os.makedirs(ann_dir)
+        open(os.path.join(img_dir, name + ".tif"), "wb").close()
+        if mask_arr is not None:
+            open(os.path.join(ann_dir, name + ".xml"), "wb").close()
+        try:
+            os.chdir(tmp)
+            ref.parse_xml_mask = fake_parse_xml_mask
+            ref.ResNet18Classifier = _OfflineResNet18Classifier
+            with contextlib.redirect_stdout(io.StringIO()), contextlib.redirect_stderr(io.StringIO()):
+                t0 = time.perf_counter()
+                ref.extract_patches(level=level, stride=stride)
+                t1 = time.perf_counter()
+                pdir = os.path.join(tmp, "data", "camelyon16", "patches", f"level_{level}", name)
+                n_png = len(os.listdir(pdir)) if os.path.isdir(pdir) else 0
+                torch.manual_seed(seed)
+                t2 = time.perf_counter()
+                if n_png:
+                    ref.extract_features(level=level)
+                t3 = time.perf_counter()
+            out = dict(stage1_s=t1 - t0, stage2_s=t3 - t2, n_png=n_png)
+            fpath = os.path.join(tmp, f"patch_features_{level}.npy")
+            if os.path.exists(fpath):
+                out["features"] = np.load(fpath)
+                out["labels"] = np.load(os.path.join(tmp, f"patch_labels_{level}.npy"))
+                out["paths"] = [os.path.basename(l.strip()) for l in open(os.path.join(tmp, f"patch_paths_{level}.txt"))]
+            else:
+                out["features"], out["labels"], out["paths"] = np.zeros((0, 512), np.float32), np.zeros((0,), np.int64), []
+        finally:
+            ref.parse_xml_mask, ref.ResNet18Classifier = orig_parse, orig_cls
+            os.chdir(cwd)
+            _slides.pop(name, None)
+    return out
 
 
 def reference_transform():
@@ -173,7 +278,8 @@ def run_reference_features(patches_rgb: list[np.ndarray], state_dict, batch: int
             model = ref.ResNet18FeatureExtractor()
         finally:
             os.chdir(cwd)
-    model.load_state_dict(state_dict)
+    if state_dict is not None:
+        model.load_state_dict(state_dict)
     model.eval()
     outs = []
     with torch.no_grad():
