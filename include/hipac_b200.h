@@ -86,6 +86,15 @@ int hipac_tile_scan(const uint8_t* d_rgb, int H, int W, int64_t pitch_bytes,
 int hipac_tile_scan_set_count_buffer(int32_t* h_count_pinned);
 int hipac_tile_scan_wait_count(void);
 
+/* Host -> device copy of `rows` rows of `row_bytes` bytes between pitched buffers (one cudaMemcpy2DAsync on `stream`).
+ * The read-once streaming pass of hipac_tile_scan needs a level image whose row pitch is a multiple of 16 bytes and whose
+ * base is 16-byte aligned (TMA bulk copies); 3*W generally is not, so callers allocate the device image with
+ * pitch = (3*W + 15) & ~15 and land the reader's [rows][3*W] host rows in it with this call (no extra pass over HBM).
+ * Replaces the `slide.read_region(...)` -> numpy hand-over of the reference's loop (src/main.py:693-697) as the point
+ * where pixels enter the path. */
+int hipac_upload_rows(void* d_dst, int64_t dst_pitch, const void* h_src, int64_t src_pitch, int64_t row_bytes, int64_t rows,
+                      void* stream);
+
 /* Pillow coefficient tables used by the kernels (known-answer hook for the CPU tests; no GPU needed).
  * scale in {2,4,8}; writes interior[2*scale], left_edge[3*scale/2], right_edge[3*scale/2] (22-bit fixed point). */
 int hipac_pillow_coeffs(int scale, int32_t* h_interior, int32_t* h_left, int32_t* h_right);

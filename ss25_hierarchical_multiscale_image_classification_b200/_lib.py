@@ -13,6 +13,9 @@ import threading
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libhipac_b200.so")
+# the same library with -DHIPAC_DEBUG_BOUNDS (device-side bounds assertions in the stage-1 kernels); loaded instead of
+# LIB_PATH when HIPAC_DEBUG_BOUNDS=1 is in the environment (tests/test_debug_bounds_gpu.py runs it in a subprocess)
+DBG_LIB_PATH = os.path.join(_HERE, "libhipac_b200_dbg.so")
 SOURCES = ["capi.cu", "tile_scan.cu", "resnet18.cu", "debug_umma.cu"]
 HEADER = os.path.join(os.path.dirname(_HERE), "include", "hipac_b200.h")
 
@@ -34,23 +37,25 @@ def _nvcc() -> str:
     return "nvcc"
 
 
-def _stale() -> bool:
-    if not os.path.exists(LIB_PATH):
+def _stale(path: str = LIB_PATH) -> bool:
+    if not os.path.exists(path):
         return True
-    t = os.path.getmtime(LIB_PATH)
+    t = os.path.getmtime(path)
     deps = [os.path.join(_CSRC, f) for f in os.listdir(_CSRC)] + [HEADER]
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile every CUDA source for sm_100a into ``libhipac_b200.so`` (in-tree)."""
-    if not force and not _stale():
-        return LIB_PATH
+def build(force: bool = False, verbose: bool = False, debug_bounds: bool = False) -> str:
+    """Compile every CUDA source for sm_100a into ``libhipac_b200.so`` (in-tree); ``debug_bounds`` builds the
+    ``-DHIPAC_DEBUG_BOUNDS`` variant ``libhipac_b200_dbg.so`` instead."""
+    out_path = DBG_LIB_PATH if debug_bounds else LIB_PATH
+    if not force and not _stale(out_path):
+        return out_path
     objs = []
-    build_dir = os.path.join(_HERE, "build")
+    build_dir = os.path.join(_HERE, "build", "dbg" if debug_bounds else "")
     os.makedirs(build_dir, exist_ok=True)
     flags = ["-std=c++17", "-O3", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a",
-             "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
+             "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"] + (["-DHIPAC_DEBUG_BOUNDS"] if debug_bounds else [])
     procs = []
     for src in SOURCES:
         obj = os.path.join(build_dir, src.replace(".cu", ".o"))
@@ -66,12 +71,12 @@ def build(force: bool = False, verbose: bool = False) -> str:
             print(out)
         if pr.returncode != 0:
             raise RuntimeError(f"nvcc failed for {src}:\n{out}")
-    cmd = [_nvcc(), "-shared", "-o", LIB_PATH + ".tmp", *objs, "-gencode", "arch=compute_100a,code=sm_100a"]
+    cmd = [_nvcc(), "-shared", "-o", out_path + ".tmp", *objs, "-gencode", "arch=compute_100a,code=sm_100a"]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}")
-    os.replace(LIB_PATH + ".tmp", LIB_PATH)
-    return LIB_PATH
+    os.replace(out_path + ".tmp", out_path)
+    return out_path
 
 
 def _declare(l):
@@ -91,6 +96,8 @@ def _declare(l):
     l.hipac_tile_scan_set_count_buffer.argtypes = [vp]
     l.hipac_tile_scan_wait_count.restype = i32
     l.hipac_tile_scan_wait_count.argtypes = []
+    l.hipac_upload_rows.restype = i32
+    l.hipac_upload_rows.argtypes = [vp, i64, vp, i64, i64, i64, vp]
     l.hipac_pillow_coeffs.restype = i32
     l.hipac_pillow_coeffs.argtypes = [i32, vp, vp, vp]
     l.hipac_normalize_lut_bf16.restype = i32
@@ -121,7 +128,7 @@ def _declare(l):
 
 EXPORTS = [
     "hipac_last_error", "hipac_abi_version", "hipac_launch_count", "hipac_tile_scan_workspace_bytes",
-    "hipac_tile_scan", "hipac_tile_scan_set_count_buffer", "hipac_tile_scan_wait_count", "hipac_pillow_coeffs", "hipac_normalize_lut_bf16", "hipac_resnet18_packed_bytes",
+    "hipac_tile_scan", "hipac_upload_rows", "hipac_tile_scan_set_count_buffer", "hipac_tile_scan_wait_count", "hipac_pillow_coeffs", "hipac_normalize_lut_bf16", "hipac_resnet18_packed_bytes",
     "hipac_resnet18_pack", "hipac_resnet18_workspace_bytes", "hipac_resnet18_forward", "hipac_resnet18_forward_dcount",
     "hipac_resnet18_conv_layer", "hipac_profile_enable", "hipac_profile_report", "hipac_debug_umma_shift", "hipac_resnet18_stem", "hipac_resnet18_conv_ds_fused",
 ]
@@ -132,11 +139,12 @@ def lib():
     global _lib
     with _lock:
         if _lib is None:
-            if not os.path.exists(LIB_PATH):
+            path = DBG_LIB_PATH if os.environ.get("HIPAC_DEBUG_BOUNDS") == "1" else LIB_PATH
+            if not os.path.exists(path):
                 raise RuntimeError(
-                    f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                    f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
                     "(the HiPAC B200 path has no CPU/PyTorch fallback)")
-            l = C.CDLL(LIB_PATH)
+            l = C.CDLL(path)
             _declare(l)
             _lib = l
     return _lib

@@ -1,5 +1,7 @@
 // Error reporting, launch counting and the optional per-kernel CUDA-event profiler of the C ABI.
 #include <map>
+#include <mutex>
+#include <utility>
 #include <vector>
 
 #include "common.cuh"
@@ -9,6 +11,36 @@ static thread_local std::string g_last_error;
 static thread_local long long g_launches = 0;
 void set_error(const std::string& msg) { g_last_error = msg; }
 void count_launch(int n) { g_launches += n; }
+
+int ensure_dyn_smem_impl(const void* func, int bytes) {
+  static std::mutex mu;
+  static std::map<std::pair<const void*, int>, int> done;   // (kernel, device) -> bytes already opted in
+  int dev = 0;
+  HIPAC_CHECK_CUDA(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lk(mu);
+  auto it = done.find({func, dev});
+  if (it != done.end() && it->second >= bytes) return 0;
+  HIPAC_CHECK_CUDA(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  done[{func, dev}] = bytes;
+  return 0;
+}
+
+int device_sm_count(int* sms) {
+  static std::mutex mu;
+  static int cache[64] = {};
+  int dev = 0;
+  HIPAC_CHECK_CUDA(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lk(mu);
+  if (dev < 64 && cache[dev]) {
+    *sms = cache[dev];
+    return 0;
+  }
+  int n = 0;
+  HIPAC_CHECK_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+  if (dev < 64) cache[dev] = n;
+  *sms = n;
+  return 0;
+}
 
 // ---- profiler: cudaEvent pairs recorded on the launching stream around each kernel -------------
 struct ProfRecord {

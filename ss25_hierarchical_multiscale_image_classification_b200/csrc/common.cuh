@@ -44,6 +44,29 @@ class ProfileScope {
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// Per-DEVICE one-time state (several GPUs may be driven from one process, from several threads):
+//   ensure_dyn_smem  cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device attribute of a kernel
+//   device_sm_count  SM count of the current device
+int ensure_dyn_smem_impl(const void* func, int bytes);
+template <typename F>
+static inline int ensure_dyn_smem(F* func, int bytes) { return ensure_dyn_smem_impl(reinterpret_cast<const void*>(func), bytes); }
+int device_sm_count(int* sms);
+
+// Device-side bounds assertions of the stage-1 kernels (compute-sanitizer is not available on the B200 pool): compiled
+// in only with -DHIPAC_DEBUG_BOUNDS (libhipac_b200_dbg.so, exercised by tests/test_debug_bounds_gpu.py).
+#ifdef HIPAC_DEBUG_BOUNDS
+#define HIPAC_DEV_ASSERT(cond)                                                                             \
+  do {                                                                                                     \
+    if (!(cond)) {                                                                                         \
+      printf("hipac bounds assertion failed: %s (%s:%d, block %d thread %d)\n", #cond, __FILE__, __LINE__, \
+             (int)blockIdx.x, (int)threadIdx.x);                                                           \
+      __trap();                                                                                            \
+    }                                                                                                      \
+  } while (0)
+#else
+#define HIPAC_DEV_ASSERT(cond) ((void)0)
+#endif
+
 constexpr int OUT = 224;  // network input size (reference src/main.py:814)
 
 }  // namespace hipac

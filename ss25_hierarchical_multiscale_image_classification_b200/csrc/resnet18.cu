@@ -10,6 +10,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <vector>
 
 #include "common.cuh"
@@ -367,7 +368,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 static EncodeIm2colFn g_encode_im2col = nullptr;
 static EncodeTiledFn g_encode_tiled = nullptr;
-static int g_num_sms = 0;
+static thread_local int g_num_sms = 0;   // SM count of the CURRENT device, refreshed by init_driver_api() on every entry
 static bool g_use_fused_stem = true;   // HIPAC_FUSED_STEM=0 runs conv1 and the max pool as two kernels
 static bool g_fuse_downsample = true; // HIPAC_FUSE_DS=0 runs the 1x1 projection shortcuts as separate kernels
 static bool g_use_row_kernels = true;  // HIPAC_CONV_ROWS=0 forces the im2col kernel everywhere (A/B comparison)
@@ -375,28 +376,32 @@ static bool g_use_row_kernels = true;  // HIPAC_CONV_ROWS=0 forces the im2col ke
 // A/B switches for measurements; read once (the workspace size depends on them).
 static bool g_boustrophedon = true;   // alternate the tile order from layer to layer (A/B switch: HIPAC_BOUSTROPHEDON=0)
 static void read_env_flags() {
-  static bool done = false;
-  if (done) return;
-  done = true;
-  if (const char* e = getenv("HIPAC_CONV_ROWS")) g_use_row_kernels = atoi(e) != 0;
-  if (const char* e = getenv("HIPAC_FUSED_STEM")) g_use_fused_stem = atoi(e) != 0;
-  if (const char* e = getenv("HIPAC_FUSE_DS")) g_fuse_downsample = atoi(e) != 0;
-  if (const char* e = getenv("HIPAC_BOUSTROPHEDON")) g_boustrophedon = atoi(e) != 0;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    if (const char* e = getenv("HIPAC_CONV_ROWS")) g_use_row_kernels = atoi(e) != 0;
+    if (const char* e = getenv("HIPAC_FUSED_STEM")) g_use_fused_stem = atoi(e) != 0;
+    if (const char* e = getenv("HIPAC_FUSE_DS")) g_fuse_downsample = atoi(e) != 0;
+    if (const char* e = getenv("HIPAC_BOUSTROPHEDON")) g_boustrophedon = atoi(e) != 0;
+  });
 }
 
+// Called at the top of every entry point: driver entry points once per process, the SM count for the CURRENT device.
 static int init_driver_api() {
-  if (g_encode_im2col && g_encode_tiled && g_num_sms) return 0;
-  cudaDriverEntryPointQueryResult q;
-  void* fn = nullptr;
-  HIPAC_CHECK_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &fn, cudaEnableDefault, &q));
-  HIPAC_REQUIRE(fn && q == cudaDriverEntryPointSuccess, "driver lacks cuTensorMapEncodeIm2col");
-  g_encode_im2col = (EncodeIm2colFn)fn;
-  HIPAC_CHECK_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
-  HIPAC_REQUIRE(fn && q == cudaDriverEntryPointSuccess, "driver lacks cuTensorMapEncodeTiled");
-  g_encode_tiled = (EncodeTiledFn)fn;
-  int dev = 0;
-  HIPAC_CHECK_CUDA(cudaGetDevice(&dev));
-  HIPAC_CHECK_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+  static std::mutex mu;
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    if (!(g_encode_im2col && g_encode_tiled)) {
+      cudaDriverEntryPointQueryResult q;
+      void* fn = nullptr;
+      HIPAC_CHECK_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &fn, cudaEnableDefault, &q));
+      HIPAC_REQUIRE(fn && q == cudaDriverEntryPointSuccess, "driver lacks cuTensorMapEncodeIm2col");
+      g_encode_im2col = (EncodeIm2colFn)fn;
+      HIPAC_CHECK_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+      HIPAC_REQUIRE(fn && q == cudaDriverEntryPointSuccess, "driver lacks cuTensorMapEncodeTiled");
+      g_encode_tiled = (EncodeTiledFn)fn;
+    }
+  }
+  if (int e = device_sm_count(&g_num_sms)) return e;
   read_env_flags();
   return 0;
 }
@@ -466,12 +471,7 @@ template <int BN, int KC, int W, int R, bool RESIDENT>
 static int launch_rows_t(const uint8_t* d_packed, const PackedLayout& L, int layer, const void* in, const void* residual, void* out,
                          int n, bool relu, cudaStream_t stream, const char* name) {
   using Cfg = RowCfg<BN, KC, W, R, RESIDENT>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    HIPAC_CHECK_CUDA(cudaFuncSetAttribute(k_conv3x3_rows<BN, KC, W, R, RESIDENT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          Cfg::kSmemBytes));
-    attr_set = true;
-  }
+  if (int e = ensure_dyn_smem(k_conv3x3_rows<BN, KC, W, R, RESIDENT>, Cfg::kSmemBytes)) return e;
   CUtensorMap tmA, tmB;
   if (int e = make_region_map(&tmA, in, n, W, W, KC * 64, R)) return e;
   if (int e = make_weight_map(&tmB, d_packed + L.w_off[layer], BN, 9 * KC * 64, BN)) return e;
@@ -493,11 +493,7 @@ static int launch_rows_t(const uint8_t* d_packed, const PackedLayout& L, int lay
 
 // Fused conv1 + BN + ReLU + maxpool on the S2D16 batch -> [n][56][56][64].
 static int run_stem(const uint8_t* d_packed, const PackedLayout& L, const void* in, void* out, int n, cudaStream_t stream) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    HIPAC_CHECK_CUDA(cudaFuncSetAttribute(k_conv1_pool, cudaFuncAttributeMaxDynamicSharedMemorySize, kStemSmem));
-    attr_set = true;
-  }
+  if (int e = ensure_dyn_smem(k_conv1_pool, kStemSmem)) return e;
   CUtensorMap tmA, tmB;
   {
     cuuint64_t dims[4] = {16, (cuuint64_t)kS2dW, 112, (cuuint64_t)n};
@@ -532,11 +528,7 @@ template <int BN>
 static int launch_conv_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvParams& p, cudaStream_t stream,
                          const char* name, double flops, const CUtensorMap* tmA2 = nullptr) {
   using Cfg = ConvCfg<BN>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    HIPAC_CHECK_CUDA(cudaFuncSetAttribute(k_conv_umma<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    attr_set = true;
-  }
+  if (int e = ensure_dyn_smem(k_conv_umma<BN>, Cfg::kSmemBytes)) return e;
   const int tiles = p.num_m_tiles * p.num_n_tiles;
   const int grid = tiles < g_num_sms ? tiles : g_num_sms;
   {

@@ -2,6 +2,9 @@
 // Replaces the hot loop of the reference's extract_patches (src/main.py:682-727) plus the
 // Resize/ToTensor/Normalize of its feature-extraction transform (src/main.py:812-818).
 // See include/hipac_b200.h for the contract and DESIGN.md for the kernels' rooflines.
+#include <atomic>
+#include <mutex>
+
 #include "common.cuh"
 #include "pillow_coeffs.h"
 #include "tile_scan_shared.cuh"
@@ -36,10 +39,15 @@ void host_normalize_lut_bf16(uint16_t* lut) {
     }
 }
 
+// Once per device, under a mutex: the tables are copied on the caller's stream and the stream is synchronised BEFORE the
+// device is marked done, and a second thread / stream asking meanwhile blocks on the mutex -- so no launch on any stream
+// can read the __constant__ tables before they have landed.
 static int upload_constants(cudaStream_t stream) {
+  static std::mutex mu;
   static bool done[64] = {};
   int dev = 0;
   HIPAC_CHECK_CUDA(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lk(mu);
   if (dev < 64 && done[dev]) return 0;
   static CoeffSet h_coef[4];
   static uint16_t h_lut[768];
@@ -152,43 +160,81 @@ __global__ void __launch_bounds__(256) k_stats_direct(ScanParams p, uint8_t* __r
 }
 
 // ------------------------------------------------------------------------------------------
-// compaction: stable (emission-order) prefix sum over the candidate flags, one CTA
+// compaction: stable (emission-order) prefix sum over the candidate flags.
+//   Blocks of 1024 candidates.  k_compact_count leaves the survivors per block in block_tot; in k_compact every CTA sums
+//   the totals of the blocks before it (a few hundred values even for a 100k x 100k level) and scatters its own block with
+//   a ballot/popc scan -- no inter-CTA waiting, any number of candidates.  With one block the count kernel is skipped.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) k_compact(ScanParams p, const uint8_t* __restrict__ flags, int n_cand,
-                                                  int32_t* __restrict__ coords, uint8_t* __restrict__ labels,
-                                                  int32_t* __restrict__ src_idx, int32_t* __restrict__ count,
-                                                  int capacity, int keep_all) {
+constexpr int kCompactBlock = 1024;
+
+__global__ void __launch_bounds__(kCompactBlock) k_compact_count(const uint8_t* __restrict__ flags, int n_cand, int keep_all,
+                                                                int32_t* __restrict__ block_tot) {
+  const int idx = blockIdx.x * kCompactBlock + threadIdx.x;
+  const int keep = idx < n_cand ? ((flags[idx] & 1) | keep_all) : 0;
+  const int n = __syncthreads_count(keep);
+  if (threadIdx.x == 0) block_tot[blockIdx.x] = n;
+}
+
+__global__ void __launch_bounds__(kCompactBlock) k_compact(ScanParams p, const uint8_t* __restrict__ flags, int n_cand,
+                                                          int32_t* __restrict__ coords, uint8_t* __restrict__ labels,
+                                                          int32_t* __restrict__ src_idx, int32_t* __restrict__ count,
+                                                          int capacity, int keep_all, const int32_t* __restrict__ block_tot) {
   __shared__ int warp_tot[32];
-  __shared__ int base;
+  __shared__ int s_base;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (threadIdx.x == 0) base = 0;
+  // ---- survivors in the blocks before this one ----
+  int part = 0;
+  for (int b = threadIdx.x; b < (int)blockIdx.x; b += kCompactBlock) part += block_tot[b];
+  part = __reduce_add_sync(0xffffffffu, part);
+  if (lane == 0) warp_tot[warp] = part;
   __syncthreads();
-  for (int start = 0; start < n_cand; start += 1024) {
-    const int idx = start + threadIdx.x;
-    const uint8_t f = idx < n_cand ? flags[idx] : 0;
-    const int keep = idx < n_cand ? ((f & 1) | keep_all) : 0;
-    const unsigned b = __ballot_sync(0xffffffffu, keep);
-    const int pre = __popc(b & ((1u << lane) - 1));
-    if (lane == 0) warp_tot[warp] = __popc(b);
-    __syncthreads();
-    int woff = 0;
-    for (int w = 0; w < warp; w++) woff += warp_tot[w];
-    const int slot = base + woff + pre;
-    if (keep && slot < capacity) {
-      const int ix = idx / p.ny, iyl = idx - ix * p.ny;
-      coords[2 * slot + 0] = ix * p.S;
-      coords[2 * slot + 1] = (p.iy_begin + iyl) * p.S;
-      labels[slot] = (f >> 1) & 1;
-      src_idx[slot] = idx;
-    }
-    __syncthreads();
-    if (threadIdx.x == 1023) base = slot + keep;
-    __syncthreads();
-  }
   if (threadIdx.x == 0) {
-    count[0] = base;
+    int t = 0;
+    for (int w = 0; w < 32; w++) t += warp_tot[w];
+    s_base = t;
+  }
+  __syncthreads();
+  const int base = s_base;
+  __syncthreads();
+  // ---- this block ----
+  const int idx = blockIdx.x * kCompactBlock + threadIdx.x;
+  const uint8_t f = idx < n_cand ? flags[idx] : 0;
+  const int keep = idx < n_cand ? ((f & 1) | keep_all) : 0;
+  const unsigned b = __ballot_sync(0xffffffffu, keep);
+  const int pre = __popc(b & ((1u << lane) - 1));
+  if (lane == 0) warp_tot[warp] = __popc(b);
+  __syncthreads();
+  int woff = 0, tot = 0;
+  for (int w = 0; w < 32; w++) {
+    woff += w < warp ? warp_tot[w] : 0;
+    tot += warp_tot[w];
+  }
+  const int slot = base + woff + pre;
+  if (keep && slot < capacity) {
+    const int ix = idx / p.ny, iyl = idx - ix * p.ny;
+    coords[2 * slot + 0] = ix * p.S;
+    coords[2 * slot + 1] = (p.iy_begin + iyl) * p.S;
+    labels[slot] = (f >> 1) & 1;
+    src_idx[slot] = idx;
+  }
+  if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) {
+    count[0] = base + tot;
     count[1] = n_cand;
   }
+}
+
+// flags -> compacted survivors (one or two launches); block_tot holds one int per 1024 candidates
+static int launch_compact(const ScanParams& p, const uint8_t* flags, int n_cand, int32_t* d_coords, uint8_t* d_labels,
+                          int32_t* src_idx, int32_t* d_count, int capacity, int keep_all, int32_t* block_tot, cudaStream_t stream) {
+  const int nb = (n_cand + kCompactBlock - 1) / kCompactBlock;
+  ProfileScope ps("compact", stream, (double)n_cand);
+  if (nb > 1) {
+    k_compact_count<<<nb, kCompactBlock, 0, stream>>>(flags, n_cand, keep_all, block_tot);
+    count_launch(1);
+  }
+  k_compact<<<nb, kCompactBlock, 0, stream>>>(p, flags, n_cand, d_coords, d_labels, src_idx, d_count, capacity, keep_all, block_tot);
+  count_launch(1);
+  return 0;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -305,11 +351,16 @@ __global__ void __launch_bounds__(256) k_resample_direct(ScanParams p, OutParams
 // host buffer and an event is recorded, so the caller can size the next stage while the (much longer) resample /
 // gather kernels of this call are still running.
 static thread_local int32_t* g_count_host = nullptr;   // set by hipac_tile_scan_set_count_buffer
-static thread_local cudaEvent_t g_count_event = nullptr;
+static thread_local cudaEvent_t g_count_events[64] = {};   // one per device: an event belongs to the device it was created on
+static thread_local cudaEvent_t g_count_event = nullptr;   // the event of this thread's most recent scan
 
 static int publish_count(const int32_t* d_count, cudaStream_t stream) {
   if (!g_count_host) return 0;
-  if (!g_count_event) HIPAC_CHECK_CUDA(cudaEventCreateWithFlags(&g_count_event, cudaEventDisableTiming));
+  int dev = 0;
+  HIPAC_CHECK_CUDA(cudaGetDevice(&dev));
+  HIPAC_REQUIRE(dev < 64, "device index above 63");
+  if (!g_count_events[dev]) HIPAC_CHECK_CUDA(cudaEventCreateWithFlags(&g_count_events[dev], cudaEventDisableTiming));
+  g_count_event = g_count_events[dev];
   HIPAC_CHECK_CUDA(cudaMemcpyAsync(g_count_host, d_count, 8, cudaMemcpyDeviceToHost, stream));
   HIPAC_CHECK_CUDA(cudaEventRecord(g_count_event, stream));
   return 0;
@@ -354,7 +405,8 @@ extern "C" size_t hipac_tile_scan_workspace_bytes(int H, int W, int P, int S, in
   int nx, ny;
   if (scan_geometry(H, W, P, S, iy_begin, iy_end, &nx, &ny)) return 0;
   const size_t n_cand = (size_t)nx * ny;
-  size_t b = align_up(n_cand, 256) + align_up(n_cand * 4, 256);  // flags + src_idx
+  size_t b = align_up(n_cand, 256) + align_up(n_cand * 4, 256) +                      // flags + src_idx
+             align_up(((n_cand + kCompactBlock - 1) / kCompactBlock) * 4, 256);        // survivors per compaction block
   if (mode != HIPAC_SCAN_DIRECT) {
     ScanParams p{};
     p.H = H, p.W = W, p.P = P, p.S = S, p.nx = nx, p.ny = ny, p.iy_begin = iy_begin;
@@ -398,6 +450,8 @@ extern "C" int hipac_tile_scan(const uint8_t* d_rgb, int H, int W, int64_t pitch
   ws += align_up((size_t)n_cand, 256);
   int32_t* src_idx = (int32_t*)ws;
   ws += align_up((size_t)n_cand * 4, 256);
+  int32_t* block_tot = (int32_t*)ws;
+  ws += align_up((size_t)((n_cand + kCompactBlock - 1) / kCompactBlock) * 4, 256);
 
   if (n_cand == 0) {
     HIPAC_CHECK_CUDA(cudaMemsetAsync(d_count, 0, 8, stream));
@@ -408,17 +462,14 @@ extern "C" int hipac_tile_scan(const uint8_t* d_rgb, int H, int W, int64_t pitch
   HIPAC_REQUIRE(mode != HIPAC_SCAN_FUSED || fused_ok,
                 "fused scan needs stride % (P/224) == 0, gcd(stride, P) % 32 == 0 and a 16-byte aligned image");
   if (mode != HIPAC_SCAN_DIRECT && fused_ok) {
-    return fused_scan_impl(p, o, flags, src_idx, d_coords, d_labels, d_count, capacity, ws, stream, keep_all);
+    return fused_scan_impl(p, o, flags, src_idx, block_tot, d_coords, d_labels, d_count, capacity, ws, stream, keep_all);
   }
   {
     ProfileScope ps("stats_direct", stream, 0.0);
     k_stats_direct<<<n_cand, 256, 0, stream>>>(p, flags);
   }
-  {
-    ProfileScope ps("compact", stream, (double)n_cand);
-    k_compact<<<1, 1024, 0, stream>>>(p, flags, n_cand, d_coords, d_labels, src_idx, d_count, capacity, keep_all);
-  }
-  count_launch(2);
+  count_launch(1);
+  if (int e = launch_compact(p, flags, n_cand, d_coords, d_labels, src_idx, d_count, capacity, keep_all, block_tot, stream)) return e;
   if (int e = publish_count(d_count, stream)) return e;
   if ((d_batch_u8 || d_batch) && capacity > 0) {
     dim3 grid((unsigned)min(n_cand, capacity), OUT);
@@ -427,6 +478,16 @@ extern "C" int hipac_tile_scan(const uint8_t* d_rgb, int H, int W, int64_t pitch
     count_launch(1);
   }
   HIPAC_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int hipac_upload_rows(void* d_dst, int64_t dst_pitch, const void* h_src, int64_t src_pitch, int64_t row_bytes,
+                                 int64_t rows, void* stream) {
+  HIPAC_REQUIRE(d_dst && h_src, "null pointer");
+  HIPAC_REQUIRE(row_bytes >= 0 && rows >= 0 && dst_pitch >= row_bytes && src_pitch >= row_bytes, "pitch smaller than a row");
+  if (row_bytes == 0 || rows == 0) return 0;
+  HIPAC_CHECK_CUDA(cudaMemcpy2DAsync(d_dst, (size_t)dst_pitch, h_src, (size_t)src_pitch, (size_t)row_bytes, (size_t)rows,
+                                     cudaMemcpyHostToDevice, (cudaStream_t)stream));
   return 0;
 }
 

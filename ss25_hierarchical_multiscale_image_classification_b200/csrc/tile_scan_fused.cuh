@@ -27,6 +27,7 @@ struct FusedGeom {
   uint32_t* cell_sum;      // [ncy][ncx]
   uint32_t* cell_any;      // [ncy][ncx]
   uint8_t* plane[3][3];    // [vkind][hkind], kinds: 0 interior, 1 top/left clamp, 2 bottom/right clamp
+  const uint8_t *ws_lo, *ws_hi;   // the workspace range the planes live in (incl. the tail pad): bounds of every plane read
 };
 
 static inline int gcd_int(int a, int b) {
@@ -495,6 +496,7 @@ __global__ void __launch_bounds__(128) k_gather(ScanParams p, FusedGeom G, OutPa
                                                 const int32_t* __restrict__ count, int capacity) {
   const int slot = blockIdx.x, jp0 = blockIdx.y * kGatherPairs;
   if (slot >= min(count[0], capacity)) return;
+  HIPAC_DEV_ASSERT(slot < capacity);
   __shared__ uint32_t ring[2 * kGatherPairs][2];   // ring pixels (3 bytes) of the CTA's 16 rows: [row][left, right]
   const int x = coords[2 * slot], y = coords[2 * slot + 1];
   const int X = threadIdx.x;
@@ -522,6 +524,7 @@ __global__ void __launch_bounds__(128) k_gather(ScanParams p, FusedGeom G, OutPa
         const int vk = j == 0 ? 1 : (j == OUT - 1 ? 2 : 0);
         const size_t row = vk == 0 ? (size_t)(J0 + j) : (size_t)iyl;
         const uint8_t* q = G.plane[vk][1 + side] + (row * G.nx + ix) * 3;
+        HIPAC_DEV_ASSERT(q >= G.ws_lo && q + 3 <= G.ws_hi && ix < (size_t)G.nx && row < (size_t)(vk == 0 ? G.Dh : G.ny));
         v = q[0] | ((uint32_t)q[1] << 8) | ((uint32_t)q[2] << 16);
       }
       ring[rr][side] = v;
@@ -557,6 +560,8 @@ __global__ void __launch_bounds__(128) k_gather(ScanParams p, FusedGeom G, OutPa
     const uint32_t* aw = reinterpret_cast<const uint32_t*>(a - (sh >> 3));
     uint32_t w[4];
     if (!F1 || reinterpret_cast<const uint8_t*>(aw + 4) <= img_end) {
+      if (F1) HIPAC_DEV_ASSERT(reinterpret_cast<const uint8_t*>(aw) >= p.rgb);
+      else HIPAC_DEV_ASSERT(reinterpret_cast<const uint8_t*>(aw) >= G.ws_lo && reinterpret_cast<const uint8_t*>(aw + 4) <= G.ws_hi);
 #pragma unroll
       for (int k = 0; k < 4; k++) w[k] = __ldg(aw + k);
     } else {                                    // last bytes of the level image: never read past the buffer
@@ -630,11 +635,7 @@ static int launch_planes(const ScanParams& p, const FusedGeom& G, cudaStream_t s
   constexpr int CI = plane_ci(F), RJ = plane_rj(F);
   const size_t smem = (size_t)kPlaneStages * kPlaneG * plane_rowcap(F) + 2 * (CI + 2 * (CI / 4 + 2)) * sizeof(int) +
                       (size_t)kPlaneG * 256 * plane_ipt(F);
-  static bool attr = false;
-  if (!attr) {
-    HIPAC_CHECK_CUDA(cudaFuncSetAttribute(k_downsample_planes<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = true;
-  }
+  if (int e = ensure_dyn_smem(k_downsample_planes<F>, (int)smem)) return e;
   dim3 grid((G.Dw + CI - 1) / CI, (G.Dh + RJ - 1) / RJ);
   ProfileScope ps("downsample_planes", stream, (double)p.H * p.W * 3);
   k_downsample_planes<F><<<grid, 256, smem, stream>>>(p, G);
@@ -657,14 +658,15 @@ static bool stream_applicable(const ScanParams& p, const FusedGeom& G) {
 template <int F>
 static int launch_scan_planes_f(const ScanParams& p, const FusedGeom& G, cudaStream_t stream) {
   const size_t smem = (size_t)kStreamWarps * kStreamStages * (kStreamRows * kStreamRowBytes + 8);
-  static int sms = 0, per_sm = 0;
-  if (!sms) {
-    int dev = 0;
-    HIPAC_CHECK_CUDA(cudaGetDevice(&dev));
-    HIPAC_CHECK_CUDA(cudaFuncSetAttribute(k_scan_planes<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int sms = 0;
+  if (int e = ensure_dyn_smem(k_scan_planes<F>, (int)smem)) return e;
+  if (int e = device_sm_count(&sms)) return e;
+  static std::atomic<int> per_sm_cached{0};   // a property of the kernel image and the architecture, equal on every B200
+  int per_sm = per_sm_cached.load();
+  if (!per_sm) {
     HIPAC_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_scan_planes<F>, kStreamWarps * 32, smem));
-    HIPAC_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     if (per_sm < 1) per_sm = 1;
+    per_sm_cached.store(per_sm);
   }
   StreamGeom Z;
   Z.n_strips = (G.Dw + kStripUnits * (8 / F) - 1) / (kStripUnits * (8 / F));
@@ -689,7 +691,7 @@ static int launch_scan_planes(const ScanParams& p, const FusedGeom& G, cudaStrea
   return launch_scan_planes_f<8>(p, G, stream);
 }
 
-static int fused_scan_impl(const ScanParams& p, const OutParams& o, uint8_t* flags, int32_t* src_idx, int32_t* d_coords,
+static int fused_scan_impl(const ScanParams& p, const OutParams& o, uint8_t* flags, int32_t* src_idx, int32_t* block_tot, int32_t* d_coords,
                            uint8_t* d_labels, int32_t* d_count, int capacity, uint8_t* ws, cudaStream_t stream, int keep_all) {
   FusedGeom G;
   if (!fused_geometry(p, &G)) {
@@ -700,11 +702,13 @@ static int fused_scan_impl(const ScanParams& p, const OutParams& o, uint8_t* fla
   G.cell_sum = reinterpret_cast<uint32_t*>(ws);
   G.cell_any = reinterpret_cast<uint32_t*>(ws + cell_bytes);
   ws += 2 * cell_bytes;
+  G.ws_lo = ws;
   for (int v = 0; v < 3; v++)
     for (int h = 0; h < 3; h++) {
       G.plane[v][h] = G.f > 1 ? ws : nullptr;
       if (G.f > 1) ws += fused_plane_bytes(G, v, h);
     }
+  G.ws_hi = ws + 1024;   // the tail pad hipac_tile_scan_workspace_bytes adds (the gather reads whole aligned words)
   const int n_cand = p.nx * p.ny;
   HIPAC_CHECK_CUDA(cudaMemsetAsync(G.cell_sum, 0, 2 * cell_bytes, stream));
   const bool stream_ok = stream_applicable(p, G);
@@ -730,11 +734,8 @@ static int fused_scan_impl(const ScanParams& p, const OutParams& o, uint8_t* fla
     ProfileScope ps("patch_flags", stream, 0.0);
     k_patch_flags<<<(n_cand + 255) / 256, 256, 0, stream>>>(p, G, flags, n_cand);
   }
-  {
-    ProfileScope ps("compact", stream, (double)n_cand);
-    k_compact<<<1, 1024, 0, stream>>>(p, flags, n_cand, d_coords, d_labels, src_idx, d_count, capacity, keep_all);
-  }
-  count_launch(2);
+  count_launch(1);
+  if (int e = launch_compact(p, flags, n_cand, d_coords, d_labels, src_idx, d_count, capacity, keep_all, block_tot, stream)) return e;
   if (int e = publish_count(d_count, stream)) return e;
   if ((o.batch_u8 || o.batch) && capacity > 0) {
     if (stream_ok) {

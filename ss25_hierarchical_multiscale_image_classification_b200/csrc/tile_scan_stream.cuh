@@ -245,9 +245,15 @@ __global__ void __launch_bounds__(kStreamWarps * 32) k_scan_planes(ScanParams p,
       else ptx::mbar_arrive(&bars[st % NS]);
     }
     __syncwarp();
-    if (valid) bulk_copy_g2s(buf + lane * kStreamRowBytes + (cbeg - A0), p.rgb + (int64_t)r * p.pitch + cbeg, (uint32_t)copy_bytes, &bars[st % NS]);
+    if (valid) {
+      HIPAC_DEV_ASSERT(cbeg >= A0 && (cbeg - A0) + copy_bytes <= kStreamRowBytes && (copy_bytes & 15) == 0);
+      HIPAC_DEV_ASSERT((int64_t)r * p.pitch + cbeg + copy_bytes <= (int64_t)p.H * p.pitch);
+      bulk_copy_g2s(buf + lane * kStreamRowBytes + (cbeg - A0), p.rgb + (int64_t)r * p.pitch + cbeg, (uint32_t)copy_bytes, &bars[st % NS]);
+    }
   };
 
+  HIPAC_DEV_ASSERT(lane_off >= 0 && lane_off + 32 <= kStreamRowBytes && (lane_off & 7) == 0);
+  HIPAC_DEV_ASSERT(!has_task || (v_off >= 0 && v_off + 3 * NE <= kStreamRowBytes));
   int Uv[NH], Sv[NH], Up[NH], Tt[NH], Bt[NH];
 #pragma unroll
   for (int e = 0; e < NH; e++) Uv[e] = Sv[e] = Up[e] = Tt[e] = Bt[e] = 0;
@@ -391,6 +397,7 @@ __global__ void __launch_bounds__(kStreamWarps * 32) k_scan_planes(ScanParams p,
       // ---- end of block J: D row J-1 = U(J-1) + V(J) ----
       if (q >= 1) {
         const size_t jr = (size_t)(J - 1 - G.Jbase);
+        HIPAC_DEV_ASSERT(J - 1 >= G.Jbase && jr < (size_t)G.Dh);
 #pragma unroll
         for (int e = 0; e < NH; e++) {
           const uint8_t v = (uint8_t)((Up[e] + 2 * F * Sv[e] - Uv[e] + RND) >> SHIFT);

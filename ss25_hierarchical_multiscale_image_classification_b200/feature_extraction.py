@@ -13,8 +13,12 @@ What differs from the reference, on purpose:
   * weights: the reference builds an ImageNet-pretrained ``ResNet18Classifier`` (needs the network) and
     then copies nothing from it because the key namespaces are disjoint (``src/main.py:852-859``), so
     its features come from ``ResNet18FeatureExtractor()``'s own weights.  This function uses exactly
-    those: the checkpoint at ``src/models/{model_path}`` if present, else seeded-random init
-    (``seed=`` argument; the reference's init is unseeded).
+    those: ``ResNet18FeatureExtractor()`` with its DEFAULT weight path (``src/models/resnet18_patch_classifier.pth``
+    if present, else seeded-random init; ``seed=`` argument, the reference's init is unseeded).  ``model_path`` is
+    accepted for signature compatibility; in the reference it only selects the classifier checkpoint whose weights
+    never reach the feature model.
+  * patches must be squares of side 224, 448, 896 or 1792 (what ``extract_patches`` writes); the reference's
+    ``Resize`` would accept any PNG size.
   * row order follows the sorted path list instead of the reference's unseeded shuffle; the paths file
     identifies rows either way.
 
@@ -89,7 +93,7 @@ def extract_features(level=3, model_path="resnet18_patch_classifier.pth", *, dev
           f"{patch_dir}, which exists: {os.path.exists(patch_dir)}")
     if seed is not None:
         torch.manual_seed(seed)
-    model = ResNet18FeatureExtractor(weight_path=model_path)
+    model = ResNet18FeatureExtractor()   # default weight path, as the reference does (src/main.py:839); model_path only names the classifier checkpoint there
     packed = _features.pack_resnet18(model._tv_state(), device)
     feats = []
     for i in range(0, len(paths), batch_size):
@@ -127,7 +131,7 @@ def extract_features_from_slides(level=3, model_path="resnet18_patch_classifier.
     level_dir = os.path.join(cwd, "data", "camelyon16", "patches", f"level_{level}")
     if seed is not None:
         torch.manual_seed(seed)
-    model = ResNet18FeatureExtractor(weight_path=model_path)
+    model = ResNet18FeatureExtractor()   # default weight path, as the reference does (src/main.py:839); model_path only names the classifier checkpoint there
     packed = _features.pack_resnet18(model._tv_state(), device)
     opener = slide_opener or _default_opener
     all_f, all_l, all_p = [], [], []

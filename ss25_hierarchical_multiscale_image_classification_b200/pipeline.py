@@ -19,7 +19,8 @@ import torch
 
 from . import features as _features
 from . import _lib
-from .preprocessing.tensor_api import extract_patches_enqueue, extract_patches_tensor, grid_shape, patch_and_stride
+from .preprocessing.tensor_api import (alloc_level_image, extract_patches_enqueue, extract_patches_tensor, grid_shape,
+                                       patch_and_stride, upload_level_rows)
 
 
 @dataclass
@@ -91,9 +92,12 @@ class HostPipeline:
     def __init__(self, height: int, width: int, device, with_mask: bool = True, capacity: int | None = None,
                  num_classes: int = 2, sparse_mask: bool = True):
         self.device = torch.device(device)
-        self.img = torch.empty((height, width, 3), dtype=torch.uint8, device=self.device)
+        # device staging with 16-byte row pitch (the streaming pass's precondition, whatever the width)
+        self.img = alloc_level_image(height, width, self.device)
         # the device mask is kept all-zero outside the rectangles uploaded by the current step
-        self.mask = torch.zeros((height, width), dtype=torch.uint8, device=self.device) if with_mask else None
+        self.mask = alloc_level_image(height, width, self.device, channels=1) if with_mask else None
+        if self.mask is not None:
+            self.mask.zero_()
         self.copy_stream = torch.cuda.Stream(self.device)
         self.capacity = capacity
         self.num_classes = num_classes
@@ -110,7 +114,10 @@ class HostPipeline:
         self.last_h2d_bytes = 0
 
     def _upload_rect(self, mask_host, r0, r1, c0, c1):
-        self.mask[r0:r1, c0:c1].copy_(mask_host[r0:r1, c0:c1], non_blocking=True)
+        if self.mask.is_cuda and c0 == 0 and c1 == int(self.mask.shape[1]):
+            upload_level_rows(self.mask, mask_host[r0:r1], r0)          # whole rows: one 2-D DMA on the current stream
+        else:
+            self.mask[r0:r1, c0:c1].copy_(mask_host[r0:r1, c0:c1], non_blocking=True)
         self._dirty.append((r0, r1, c0, c1))
         self.last_h2d_bytes += (r1 - r0) * (c1 - c0)
 
@@ -188,8 +195,7 @@ def process_level_host(level_img_host: torch.Tensor, mask_host, level: int, pack
         for g in range(groups):
             need = min(H, (bounds[g + 1] - 1) * S + P + 8) if bounds[g + 1] > bounds[g] else done_rows
             if need > done_rows:
-                pipe.img[done_rows:need].copy_(level_img_host[done_rows:need], non_blocking=True)
-                pipe.last_h2d_bytes += (need - done_rows) * W * 3
+                pipe.last_h2d_bytes += upload_level_rows(pipe.img, level_img_host[done_rows:need], done_rows)
                 if pipe.mask is not None and mask_host is not None:
                     pipe.upload_mask_rows(mask_host, done_rows, need)   # host scan overlaps the image DMA just queued
                 done_rows = need

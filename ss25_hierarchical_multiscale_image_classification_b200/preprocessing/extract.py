@@ -11,6 +11,17 @@ the reference's own downstream code consume the output unchanged.
 The slide reader is duck-typed OpenSlide (``level_dimensions``, ``level_downsamples``,
 ``read_region``); pass ``slide_opener=`` to inject one (tests use ``SyntheticSlide``), otherwise
 ``openslide.OpenSlide`` is imported lazily.
+
+Differences on purpose:
+  * pixels are read as full-width row slabs at ``(0, int(y0 * downsample))`` and patches are cut out of the slab on the
+    GPU, where the reference issues one ``read_region((int(x * ds), int(y * ds)), level, (w, h))`` per candidate
+    (``src/main.py:693-697``).  For pyramids whose ``level_downsamples`` are exact integers (``2 ** level``: every
+    synthetic slide here, and CAMELYON16 levels whose level-0 size is divisible by ``2 ** level``) the two address the
+    same level pixels.  With a non-integer downsample (odd level-0 dimensions) ``int(x * ds)`` is not a multiple of the
+    downsample and the reader resolves the level-0 location to a level pixel by its own rounding, so a per-patch read
+    may start up to one LEVEL pixel off the slab's column ``x``; parity with the reference is only claimed (and tested)
+    for exact downsamples.
+  * a full-width RGBA ``read_region`` of a slab is a large host allocation; ``max_slab_bytes`` bounds it.
 """
 from __future__ import annotations
 
@@ -20,7 +31,7 @@ import numpy as np
 import torch
 from PIL import Image, ImageDraw
 
-from .tensor_api import extract_patches_tensor, grid_shape, patch_and_stride
+from .tensor_api import alloc_level_image, extract_patches_tensor, grid_shape, patch_and_stride, upload_level_rows
 
 
 class bcolors:  # same tags as the reference (src/main.py:35-44)
@@ -94,8 +105,13 @@ def scan_slide(slide, level: int, mask: np.ndarray | None, stride=None, patch_si
         i1 = min(ny, i0 + rows_per_slab)
         y0, y1 = i0 * S, min(height, (i1 - 1) * S + P)
         rgb = read_level_rows(slide, level, y0, y1)
-        img = torch.from_numpy(np.ascontiguousarray(rgb)).to(device)
-        m = torch.from_numpy(np.array(mask[y0:y1])).to(device) if mask is not None else None
+        # device slab with 16-byte row pitch (streaming-pass precondition), filled by one 2-D copy per buffer
+        img = alloc_level_image(y1 - y0, width, device)
+        upload_level_rows(img, np.ascontiguousarray(rgb))
+        m = None
+        if mask is not None:
+            m = alloc_level_image(y1 - y0, width, device, channels=1)
+            upload_level_rows(m, np.ascontiguousarray(mask[y0:y1]))
         # a slab that ends above the image bottom has complete data for its grid rows, so tiling it as its own
         # image (rows [0, i1-i0) of the slab) gives exactly the patches of grid rows [i0, i1)
         pb = extract_patches_tensor(img, m, level, stride=stride, patch_size=patch_size, row_range=(0, i1 - i0),
@@ -133,10 +149,16 @@ def _save_patches(rgb_level_rows, y0, coords, labels, P, width, height, prefix, 
 
 
 def _extract_one(file, wsi_dir, level_dir, annot_dir_train, annot_dir_test, level, stride, patch_size_arg, pad,
-                 slide_opener, device, max_slab_bytes):
+                 slide_opener, device, max_slab_bytes, skip_needs_both_labels=False):
     prefix = file.replace(".tif", "")
     patch_save_dir = os.path.join(level_dir, prefix)
-    if os.path.exists(patch_save_dir) and len(os.listdir(patch_save_dir)) > 0:
+    existing = os.listdir(patch_save_dir) if os.path.exists(patch_save_dir) else []
+    done = len(existing) > 0
+    if skip_needs_both_labels:
+        # extract_patches_per_slide only skips a slide that already has BOTH a *_normal.png and a *_tumor.png
+        # (reference src/main.py:286-292): a partially extracted slide is re-run (existing files are kept, 725-726)
+        done = done and any(f.endswith("_normal.png") for f in existing) and any(f.endswith("_tumor.png") for f in existing)
+    if done:
         print(f"{bcolors.INFO}[INFO]{bcolors.ENDC} Patches for {file} already extracted, skipping.")
         return None
     os.makedirs(patch_save_dir, exist_ok=True)
@@ -217,4 +239,4 @@ def extract_patches_per_slide(slide_path="tumor_109", patch_size=224, level=3, s
     level_dir = os.path.join(cwd, "data", "camelyon16", "patches", f"level_{level}")
     os.makedirs(level_dir, exist_ok=True)
     return _extract_one(file, wsi_dir, level_dir, annot_dir_train, annot_dir_test, level, stride, patch_size, pad,
-                        slide_opener or _default_opener, device, max_slab_bytes)
+                        slide_opener or _default_opener, device, max_slab_bytes, skip_needs_both_labels=True)

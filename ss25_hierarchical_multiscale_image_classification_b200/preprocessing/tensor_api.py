@@ -100,6 +100,50 @@ class PendingPatchBatch:
                           candidates=n_c, patch=self.patch, stride=self.stride, level=self.level)
 
 
+def alloc_level_image(height: int, width: int, device, channels: int = 3) -> torch.Tensor:
+    """uint8 ``[H, W, 3]`` (``channels=3``) or ``[H, W]`` (``channels=1``, lesion mask) device tensor whose row pitch is a
+    multiple of 16 bytes -- what the read-once TMA streaming pass of ``hipac_tile_scan`` needs (``3 * W`` usually is
+    not).  A view of a ``[H, pitch]`` buffer; index / slice it like any tensor."""
+    pitch = (width * channels + 15) // 16 * 16
+    buf = torch.empty((height, pitch), dtype=torch.uint8, device=device)
+    if channels == 1:
+        return buf[:, :width]
+    return buf.as_strided((height, width, channels), (pitch, channels, 1))
+
+
+def upload_level_rows(dst: torch.Tensor, src_host, r0: int = 0, stream: torch.cuda.Stream | None = None) -> int:
+    """Copy host rows ``src_host`` (``uint8 [n, W, 3]`` or ``[n, W]``, numpy or CPU tensor, row-contiguous) into rows
+    ``[r0, r0 + n)`` of a (possibly pitched) device image with ONE 2-D DMA (``hipac_upload_rows``); asynchronous when
+    the host memory is pinned.  Returns the number of payload bytes."""
+    src = torch.as_tensor(src_host)
+    if src.dtype != torch.uint8 or src.is_cuda:
+        raise ValueError("src_host must be uint8 host memory")
+    n = int(src.shape[0])
+    if n == 0:
+        return 0
+    row_bytes = int(src[0].numel())
+    if src.dim() >= 2 and src[0].numel() and not src[0].is_contiguous():
+        src = src.contiguous()
+    view = dst[r0:r0 + n]
+    if int(view.shape[0]) != n or int(view[0].numel()) != row_bytes:
+        raise ValueError(f"rows [{r0}, {r0 + n}) x {row_bytes} bytes do not fit the destination {tuple(dst.shape)}")
+    st = stream or torch.cuda.current_stream(dst.device)
+    with torch.cuda.device(dst.device):
+        _lib.check(_lib.lib().hipac_upload_rows(view.data_ptr(), int(dst.stride(0)), src.data_ptr(), int(src.stride(0)) if n > 1 else row_bytes,
+                                                row_bytes, n, st.cuda_stream), "hipac_upload_rows")
+    return row_bytes * n
+
+
+def _pitched16(t: torch.Tensor, channels: int) -> torch.Tensor:
+    """``t`` itself when its rows already start on 16-byte boundaries, else a device-side copy into a pitched buffer (one
+    extra read + write of the image: callers that own the upload should use ``alloc_level_image`` instead)."""
+    if int(t.stride(0)) % 16 == 0 and t.data_ptr() % 16 == 0:
+        return t
+    out = alloc_level_image(int(t.shape[0]), int(t.shape[1]), t.device, channels)
+    out.copy_(t)
+    return out
+
+
 def batch_shape(n: int, layout: str):
     return (n, OUT, OUT, 3) if layout == "nhwc3" else (n, OUT // 2, S2D16_WIDTH, 16)
 
@@ -141,6 +185,13 @@ def extract_patches_enqueue(level_img: torch.Tensor, lesion_mask: torch.Tensor |
         if lesion_mask.stride(1) != 1:
             lesion_mask = lesion_mask.contiguous()
     P, S = patch_and_stride(level, stride, patch_size)
+    if P > OUT and mode != "direct":
+        # the read-once streaming pass wants 16-byte aligned rows; anything else would silently take the two-pass kernels
+        with torch.cuda.device(level_img.device), torch.cuda.stream(stream or torch.cuda.current_stream(level_img.device)):
+            level_img = _pitched16(level_img, 3)
+            if lesion_mask is not None:
+                lesion_mask = _pitched16(lesion_mask, 1)
+        pitch = int(level_img.stride(0))
     nx, ny_all = grid_shape(W, H, S)
     i0, i1 = (0, ny_all) if row_range is None else (int(row_range[0]), int(row_range[1]))
     if not (0 <= i0 <= i1 <= ny_all):

@@ -24,6 +24,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 from oracle import hipac_oracle as orc  # noqa: E402
 from oracle import ref_harness as rh  # noqa: E402
 from ss25_hierarchical_multiscale_image_classification_b200.synthetic import SyntheticSlide  # noqa: E402
+sys.path.insert(0, os.path.dirname(HERE))
+from conftest import make_slide  # noqa: E402
 
 # name -> (w0, h0, seed, level, stride, with_mask)
 CASES = {
@@ -37,13 +39,17 @@ CASES = {
     "l3_no_mask":      (9000, 7000, 99, 3, None, False),      # no annotation -> all "normal"
     "l0_tiny_slide":   (1000, 800, 3, 0, None, True),         # slide smaller than one patch
     "l2_exact_fit":    (3584 * 4 // 4, 1792, 11, 2, 448, True),  # level dims multiple of P: no padding
+    # slide smaller than one patch WITH survivors: every patch is mostly white padding, the dark content decides
+    # (seed < 0 selects conftest.dark_level: uniform noise in [40, 170) instead of the synthetic tissue layout)
+    "l0_tiny_dark":    (1500, 1400, -7, 0, None, True),
+    "l1_tiny_dark":    (1300, 1000, -9, 1, None, True),       # level-1 image 650 x 500 < P = 896
 }
 N_FULL = 4   # full resized images kept per case
 
 
 def stage1_case(name):
     w0, h0, seed, level, stride, with_mask = CASES[name]
-    slide = SyntheticSlide(w0, h0, seed=seed, with_lesion=with_mask)
+    slide = make_slide(w0, h0, seed, with_mask)
     ref = rh.run_reference_extract_patches(slide, level, stride=stride, with_mask=with_mask)
     coords = np.asarray([(r[1], r[2]) for r in ref], dtype=np.int32).reshape(-1, 2)
     labels = np.asarray([r[3] for r in ref], dtype=np.uint8)
@@ -86,10 +92,15 @@ def stage2_case():
 
 def main():
     assert rh.reference_available(), "needs /root/reference"
+    only = sys.argv[1:]
     for name in CASES:
+        if only and name not in only:
+            continue
         d = stage1_case(name)
         np.savez_compressed(os.path.join(HERE, f"stage1_{name}.npz"), **d)
         print(f"{name}: {len(d['coords'])} survivors, {int(d['labels'].sum())} tumor")
+    if only and "stage2" not in only:
+        return
     d = stage2_case()
     np.savez_compressed(os.path.join(HERE, "stage2_features.npz"), **d)
     print("stage2:", d["features"].shape, "weight_abs_sum", d["weight_abs_sum"])

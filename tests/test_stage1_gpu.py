@@ -208,3 +208,75 @@ def test_pending_scans_resolve_in_any_order():
     assert len(rb) == 0 and rb.candidates == 9
     want = extract_patches_tensor(a_img, None, 3, layout="nhwc3")
     assert 0 < len(ra) == len(want) <= 20 and ra.candidates == 20 and torch.equal(ra.coords, want.coords)
+
+
+def test_many_candidates_multi_block_compaction():
+    """More than 1024 candidates: the compaction runs as several CTAs (per-block totals + per-block scatter) and must
+    still emit survivors in the reference's x-outer / y-inner order."""
+    rng = np.random.default_rng(21)
+    h, w = 1900, 2300
+    img = rng.integers(215, 256, size=(h, w, 3), dtype=np.uint8)          # hovers around the threshold: ragged keep pattern
+    img[200:1500, 300:1900] = rng.integers(0, 256, size=(1300, 1600, 3), dtype=np.uint8)
+    mask = np.zeros((h, w), np.uint8)
+    mask[900:950, 1000:1100] = 255
+    for stride, mode in ((32, "auto"), (32, "direct"), (40, "auto")):     # 72 x 60 = 4320 / 58 x 48 = 2784 candidates at P = 224
+        want = orc.extract_patches_oracle(img, mask, 3, stride=stride, want_images=False)
+        assert want["candidates"] > 2048
+        out = _run(img, mask, 3, stride, mode=mode, layout=None)
+        assert out.candidates == want["candidates"]
+        assert np.array_equal(out.coords.cpu().numpy(), want["coords"])
+        assert np.array_equal(out.labels.cpu().numpy(), want["labels"])
+    # capacity smaller than the survivor count: the count is still the true one, only `capacity` rows are written
+    from ss25_hierarchical_multiscale_image_classification_b200.preprocessing import extract_patches_enqueue
+    pend = extract_patches_enqueue(torch.from_numpy(img).cuda(), None, 3, stride=32, layout=None, capacity=1500)
+    n, n_c = (int(v) for v in pend.count.cpu().tolist())
+    want = orc.extract_patches_oracle(img, None, 3, stride=32, want_images=False)
+    assert n == len(want["coords"]) > 1500 and n_c == want["candidates"]
+    assert np.array_equal(pend.coords.cpu().numpy()[:1500], want["coords"][:1500])
+
+
+def test_unaligned_pitch_is_repitched_onto_the_streaming_pass_and_raw_abi_fallback():
+    """A contiguous [H, W, 3] tensor with 3*W % 16 != 0: the Python API re-pitches it so that the read-once streaming
+    pass runs (no silent two-pass fallback); the raw C ABI with the unaligned pitch still works through the cp.async
+    kernels.  Both equal the direct path bit for bit."""
+    from ss25_hierarchical_multiscale_image_classification_b200 import _lib
+    from ss25_hierarchical_multiscale_image_classification_b200.preprocessing import alloc_level_image, upload_level_rows
+    rng = np.random.default_rng(33)
+    h, w, level = 1300, 1501, 2
+    img = rng.integers(100, 256, size=(h, w, 3), dtype=np.uint8)
+    mask = np.zeros((h, w), np.uint8)
+    mask[400:420, 100:900] = 3
+    ref = _run(img, mask, level, None, mode="direct", layout="s2d16")
+    _lib.profile(True)
+    out = _run(img, mask, level, None, mode="auto", layout="s2d16")
+    torch.cuda.synchronize()
+    prof = _lib.profile_report()
+    _lib.profile(False)
+    assert "scan_planes" in prof and "downsample_planes" not in prof, prof.keys()
+    assert torch.equal(ref.coords, out.coords) and torch.equal(ref.labels, out.labels)
+    assert torch.equal(ref.images_u8, out.images_u8) and torch.equal(ref.batch.view(torch.int16), out.batch.view(torch.int16))
+    # pitched staging filled by the 2-D upload: same result
+    dimg, dmask = alloc_level_image(h, w, "cuda"), alloc_level_image(h, w, "cuda", channels=1)
+    assert dimg.stride(0) % 16 == 0 and dmask.stride(0) % 16 == 0
+    upload_level_rows(dimg, img[:700]), upload_level_rows(dimg, img[700:], 700)
+    upload_level_rows(dmask, mask)
+    from ss25_hierarchical_multiscale_image_classification_b200.preprocessing import extract_patches_tensor
+    up = extract_patches_tensor(dimg, dmask, level, layout="s2d16", want_u8=True)
+    assert torch.equal(ref.coords, up.coords) and torch.equal(ref.images_u8, up.images_u8) and torch.equal(ref.labels, up.labels)
+    # raw ABI, contiguous unaligned pitch, fused mode: cp.async kernels
+    l = _lib.lib()
+    t, m = torch.from_numpy(img).cuda(), torch.from_numpy(mask).cuda()
+    P, S = 448, 224
+    ny = (h + S - 1) // S
+    cap = ((w + S - 1) // S) * ny
+    coords = torch.empty((cap, 2), dtype=torch.int32, device="cuda")
+    labels = torch.empty((cap,), dtype=torch.uint8, device="cuda")
+    u8 = torch.empty((cap, 224, 224, 3), dtype=torch.uint8, device="cuda")
+    count = torch.zeros((2,), dtype=torch.int32, device="cuda")
+    wsb = l.hipac_tile_scan_workspace_bytes(h, w, P, S, 0, ny, _lib.SCAN_FUSED)
+    ws = torch.empty((wsb,), dtype=torch.uint8, device="cuda")
+    rc = l.hipac_tile_scan(t.data_ptr(), h, w, 3 * w, m.data_ptr(), w, P, S, 0, ny, coords.data_ptr(), labels.data_ptr(), u8.data_ptr(),
+                           None, 0, count.data_ptr(), cap, ws.data_ptr(), wsb, _lib.SCAN_FUSED, torch.cuda.current_stream().cuda_stream)
+    assert rc == 0, l.hipac_last_error()
+    n = int(count[0])
+    assert n == len(ref) and torch.equal(coords[:n], ref.coords) and torch.equal(u8[:n], ref.images_u8)
