@@ -210,12 +210,8 @@ def run_ours(args):
     ranks_sharing = max(1, round(world * len(os.sched_getaffinity(0)) / cpus_before))   # ranks bound to the same cores
     host_threads = max(1, min(16, len(os.sched_getaffinity(0)) // ranks_sharing))
     torch.set_num_threads(host_threads)
-    count_group = None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-        if os.environ.get("MASTER_ADDR", "127.0.0.1") in ("127.0.0.1", "localhost"):
-            os.environ.setdefault("GLOO_SOCKET_IFNAME", "lo")   # single node: do not depend on the hostname resolving
-        count_group = dist.new_group(backend="gloo")   # CPU-side exchange of the per-rank survivor counts
     ge.build()
     net = seeded_resnet18(seed=0, classifier=True)                        # random-init weights (BASELINE config)
     packed = features.pack_resnet18(net.state_dict(), dev)
@@ -225,30 +221,36 @@ def run_ours(args):
     n_cand = ((WIDTH + STRIDE - 1) // STRIDE) * (i1 - i0)
     pipe = pipeline.HostPipeline(int(img_h.shape[0]), WIDTH, dev, with_mask=True, num_classes=2)
 
+    nx = (WIDTH + STRIDE - 1) // STRIDE
+    # the exchange step (csrc/exchange.cu + one NCCL all-gather): capacity = the largest per-rank candidate count
+    ny_total = (ROWS_PER_GPU * world + STRIDE - 1) // STRIDE
+    seg_cap = nx * max(shard_rows(ny_total, world, r)[1] - shard_rows(ny_total, world, r)[0] for r in range(world))
+    xchg = sharding.SurvivorExchange(dev, seg_cap, 2, nx, STRIDE) if world > 1 else None
+    gb = pipeline.upload_group_bounds(0, seg_cap // nx, args.groups)        # e2e leg: one segment per upload row group
+    xchg_e2e = sharding.SurvivorExchange(dev, nx * (max(b - a for a, b in zip(gb, gb[1:])) + 1), 2, nx, STRIDE,
+                                         segs_per_rank=len(gb) - 1) if world > 1 else None
     last_gathered = {}
 
-    def gather(r):
-        """The path's one exchange step: all-gather of counts / coords / labels / features / logits."""
-        if world == 1:
-            last_gathered["out"] = {"coords": r.coords, "labels": r.labels, "features": r.features, "logits": r.logits}
-            return len(r)
-        coords = r.coords.to(dev).clone()
-        coords[:, 1] += y0
-        out = sharding.gather_survivors({"coords": coords, "labels": r.labels.to(dev), "features": r.features.to(dev),
-                                         "logits": r.logits.to(dev)}, sort=True, count_group=count_group)
-        last_gathered["out"] = out
-        return int(out["coords"].shape[0])
-
     def step_resident():
-        r = pipeline.process_level(img_d, msk_d, LEVEL, packed, stride=None, row_range=rows, chunk=args.chunk)
-        return gather(r), r
+        if world == 1:
+            r = pipeline.process_level(img_d, msk_d, LEVEL, packed, stride=None, row_range=rows, chunk=args.chunk)
+            last_gathered["out"] = {"coords": r.coords, "labels": r.labels, "features": r.features, "logits": r.logits}
+            return len(r), len(r)
+        # tile scan + ResNet18 enqueued without a host wait, then the one exchange step: pack (device count) ->
+        # all-gather -> index + scatter into canonical (x, y) order; the only host read of the step is the final total
+        seg = pipeline.process_level_enqueue(img_d, msk_d, LEVEL, packed, stride=None, row_range=rows, chunk=args.chunk)
+        xchg.pack(0, seg.pend.coords, seg.pend.labels, seg.features, seg.logits, seg.count, y_offset=y0)
+        xchg.merge()
+        out = xchg.result()
+        last_gathered["out"] = out
+        return int(out["coords"].shape[0]), None
 
     def step_e2e():
         # host buffers in, host buffers out: pinned H2D of image + mask (overlapped with compute by row groups),
         # D2H of coords / labels / features / logits; process_level_host synchronises before returning
         r = pipeline.process_level_host(img_h, msk_h, LEVEL, packed, pipe, stride=None, row_range=rows,
-                                        groups=args.groups, chunk=args.chunk)
-        return gather(r), r
+                                        groups=args.groups, chunk=args.chunk, exchange=xchg_e2e, y_offset=y0)
+        return len(r), len(r)
 
     def timed(fn, steps, warmup):
         for _ in range(warmup):
@@ -278,17 +280,19 @@ def run_ours(args):
     # the gathered, canonically sorted patch set of the last resident step (every rank holds the same one)
     res = {k: v.cpu().numpy() for k, v in last_gathered["out"].items()}
     order = np.lexsort((res["coords"][:, 1], res["coords"][:, 0]))
+    canonical = bool(np.array_equal(order, np.arange(len(order))))     # the exchange already delivers (x, y) order
     import zlib
     crc = 0
     for k in ("coords", "labels", "features", "logits"):
-        crc = zlib.crc32(np.ascontiguousarray(res[k][order]).tobytes(), crc)
-    ms_e2e, total_surv_e, _ = timed(step_e2e, max(2, args.steps // 2), 1)
-    n_surv = len(pb)
+        crc = zlib.crc32(np.ascontiguousarray(res[k]).tobytes(), crc)
+    ms_e2e, total_surv_e, n_e2e_rows = timed(step_e2e, max(2, args.steps // 2), 1)
+    ys = res["coords"][:, 1]
+    n_surv = pb if pb is not None else int(((ys >= i0 * STRIDE) & (ys < i1 * STRIDE)).sum())   # this rank's own survivors
 
     # per-kernel CUDA-event timing (library profiler) over 2 extra steps, off the timed region
     _lib.profile(True)
     for _ in range(2):
-        step_resident()
+        pipeline.process_level(img_d, msk_d, LEVEL, packed, stride=None, row_range=rows, chunk=args.chunk)
     torch.cuda.synchronize()
     prof = _lib.profile_report()
     _lib.profile(False)
@@ -298,7 +302,7 @@ def run_ours(args):
     conv_ms = sum(v["ms"] for v in conv.values())
     conv_flops = sum(v["work"] for v in conv.values())
     conv_tf = conv_flops / (conv_ms * 1e-3) / 1e12 if conv_ms else 0.0
-    s1 = {k: v for k, v in prof.items() if not k.startswith(("conv", "maxpool", "avgpool", "pack"))}
+    s1 = {k: v for k, v in prof.items() if not k.startswith(("conv", "maxpool", "avgpool", "pack", "exchange"))}
     s1_ms = sum(v["ms"] for v in s1.values()) / 2
     s1_bytes = img_d.numel() + msk_d.numel() + n_surv * ALGO_OUT_BYTES
     s1_written = n_surv * (S2D_BYTES + 9)                                        # what the kernels really write
@@ -344,17 +348,20 @@ def run_ours(args):
                    "candidates_per_step": n_cand * world if world == 1 else None, "survivors_per_step": total_surv,
                    "candidates_per_s": round(n_cand * world / (ms_step * 1e-3), 1),
                    "sharding": f"tile-row ranges over {world} rank(s) of one {ROWS_PER_GPU * world}-row slide (content periodic in y, period "
-                               f"{ROWS_PER_GPU}); NCCL all-gather of counts/coords/labels/features/logits + canonical sort",
+                               f"{ROWS_PER_GPU}); exchange step = device-side pack (count in the header) + ONE fixed-size NCCL all-gather + "
+                               "index/scatter kernels into canonical (x, y) order (csrc/exchange.cu); no host-side count exchange",
                    "cache": "inputs (0.8 GB image + 0.27 GB mask per GPU) exceed the 126 MB L2; no flush needed",
                    "resnet_chunk": args.chunk, "e2e_upload_groups": args.groups, "host_threads_per_rank": host_threads, "cpus_near_gpu": near_cpus},
         "e2e": {"value": round(total_surv_e / (ms_e2e * 1e-3), 1), "unit": "patches/s",
                 "h2d_bytes_per_step": int(pipe.last_h2d_bytes),
                 "h2d_note": "image rows once + the non-zero 32-row blocks of the lesion mask (host block-max scan inside the "
                             f"timed region); dense input is {int(img_h.numel() + msk_h.numel())} bytes",
-                "d2h_bytes_per_step": int(n_surv * (512 * 4 + 8 + 1) + 8), "ms_per_step": round(ms_e2e, 3)},
+                "d2h_bytes_per_step": int(n_e2e_rows * (512 * 4 + 2 * 4 + 8 + 1) + 8),
+                "d2h_note": "coords + labels + features + logits of every row this rank returns to its host (N > 1: the gathered set)",
+                "ms_per_step": round(ms_e2e, 3)},
         "gpu_launches": launches,
         "clocks": clk.summary(),
-        "patch_set_crc32": f"{crc:08x}",
+        "patch_set_crc32": f"{crc:08x}", "patch_set_in_canonical_order": canonical,
         "roofline": {"bound": "tensor", "kernel": f"conv stack: k_conv1_pool + k_conv3x3_rows + k_conv_umma ({sum(v['launches'] for v in conv.values()) // 2} launches = 20 conv layers per step)",
                      "achieved": round(conv_tf, 1),
                      "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",

@@ -153,6 +153,36 @@ int hipac_resnet18_conv_ds_fused(const void* d_packed, int num_classes, int stag
 /* Test hook: the fused stem (conv1 + folded BN + ReLU + 3x3/s2 max pool): S2D16 batch -> bf16 [n][56][56][64]. */
 int hipac_resnet18_stem(const void* d_packed, int num_classes, const void* d_in, void* d_out, int n_patches, void* stream);
 
+/* ---------------------------------------------------------------------------------------
+ * The exchange step: per-segment survivors -> ONE canonically ordered result.
+ * A segment = the outputs of one tile-scan + forward pass over a contiguous range of candidate grid rows (a rank's
+ * shard, or one row group of it): rows in emission order (x outer, y inner), count on the device.  The reference has no
+ * counterpart (nn.DataParallel only, src/main.py:839-842); the contract is array equality with a single-rank run, whose
+ * row order is the reference's loop order (src/main.py:682-683).
+ *
+ *   hipac_exchange_pack   writes segment = [1 + capacity][row_bytes] bytes: header row {count}, then per survivor
+ *                         {x, y + y_offset, label, features[512], logits[num_classes]}.  Segments of equal capacity laid
+ *                         side by side are the send / receive buffers of one fixed-size all-gather (the counts ride in
+ *                         the headers: no separate count exchange, no host round trip).
+ *   hipac_exchange_merge  num_segments segments, ordered by ascending y range (rank after rank, row group after row
+ *                         group) -> final arrays in (x, y) order: a binary search per (segment, grid column), one prefix
+ *                         sum, one scatter.  d_total[0] = number of rows (device memory; rows beyond out_capacity are
+ *                         dropped), d_total[1] = out_capacity.  stride / nx = candidate grid stride and column count.
+ * ------------------------------------------------------------------------------------- */
+#define HIPAC_FEATURE_DIM 512
+/* feat_dim is 512 (rows carry the features) or 0 (coords / labels / logits only, e.g. the heatmap of configs[3]).
+ * hipac_exchange_pack: `capacity` = rows available in the INPUT tensors (<= the segment's row capacity); min(*d_count,
+ * capacity) rows are packed.  hipac_exchange_merge: `capacity` = row capacity of every segment (segment stride =
+ * hipac_exchange_segment_bytes(capacity, ...)). */
+size_t hipac_exchange_row_bytes(int feat_dim, int num_classes);
+size_t hipac_exchange_segment_bytes(int capacity, int feat_dim, int num_classes);
+size_t hipac_exchange_workspace_bytes(int num_segments, int nx);
+int hipac_exchange_pack(const int32_t* d_coords, const uint8_t* d_labels, const float* d_feats, const float* d_logits,
+                        int feat_dim, int num_classes, const int32_t* d_count, int capacity, int y_offset, void* d_segment, void* stream);
+int hipac_exchange_merge(const void* d_segments, int num_segments, int capacity, int feat_dim, int num_classes, int stride, int nx,
+                         int32_t* d_coords, uint8_t* d_labels, float* d_feats, float* d_logits, int32_t* d_total,
+                         int out_capacity, void* d_workspace, size_t workspace_bytes, void* stream);
+
 /* Number of kernel launches issued by this library on the calling thread since the last reset
  * (bench.py's "gpu_launches"). */
 long long hipac_launch_count(int reset);

@@ -35,6 +35,35 @@ class LevelResult:
         return int(self.coords.shape[0])
 
 
+@dataclass
+class PendingLevel:
+    """One enqueued tile-scan + ResNet18 pass (a SEGMENT of the exchange step): capacity-sized device tensors plus the
+    device-side survivor counter; nothing has been waited for."""
+    pend: object                # PendingPatchBatch
+    features: torch.Tensor      # float32 [capacity, 512]
+    logits: torch.Tensor | None
+
+    @property
+    def count(self):
+        return self.pend.count
+
+    @property
+    def capacity(self):
+        return self.pend.capacity
+
+
+def process_level_enqueue(level_img, lesion_mask, level, packed, stride=None, row_range=None, chunk: int = 8192,
+                          mode: str = "auto") -> PendingLevel:
+    """Enqueue tile scan + ResNet18 of candidate grid rows ``row_range`` without any host wait (the network kernels read
+    the survivor count from device memory).  Feed the result to ``sharding.SurvivorExchange.pack``."""
+    pend = extract_patches_enqueue(level_img, lesion_mask, level, stride=stride, row_range=row_range, layout="s2d16", mode=mode)
+    if packed.num_classes > 0:
+        feats, logits = _features.classify_tensor(pend.batch, packed, chunk, count=pend.count)
+    else:
+        feats, logits = _features.extract_features_tensor(pend.batch, packed, chunk, count=pend.count), None
+    return PendingLevel(pend, feats, logits)
+
+
 def _process_rows(level_img, lesion_mask, level, packed, stride, rows, chunk, mode):
     """Tile scan + ResNet18 of one candidate-row group, enqueued back to back: the network kernels take the survivor
     count from device memory (``hipac_resnet18_forward_dcount``), so the host only learns it afterwards, to slice the
@@ -80,6 +109,44 @@ def process_level(level_img: torch.Tensor, lesion_mask, level: int, packed: _fea
     logits = torch.cat([r.logits for r in parts])[perm] if parts[0].logits is not None else None
     return LevelResult(coords[perm], torch.cat([r.labels for r in parts])[perm], torch.cat([r.features for r in parts])[perm],
                        logits, sum(r.candidates for r in parts))
+
+
+def exchange_for_level(device, width: int, rows_per_rank: int, stride: int, num_classes: int, max_candidates: int = 16384,
+                       with_features: bool = True, group=None):
+    """A ``sharding.SurvivorExchange`` sized for ``process_level_exchanged``: every rank tiles at most ``rows_per_rank``
+    candidate grid rows of a ``width``-pixel level, in row groups of at most ``max_candidates`` candidates (the batch
+    buffer is sized for the worst case: every candidate survives)."""
+    from . import sharding
+    nx = (width + stride - 1) // stride
+    rows_per_group = max(1, min(rows_per_rank, max_candidates // max(nx, 1)))
+    n_groups = max(1, (rows_per_rank + rows_per_group - 1) // rows_per_group)
+    return sharding.SurvivorExchange(device, nx * rows_per_group, num_classes, nx, stride, segs_per_rank=n_groups, group=group,
+                                     with_features=with_features)
+
+
+def process_level_exchanged(level_img, lesion_mask, level: int, packed: _features.PackedResNet18, exchange, stride=None,
+                            row_range=None, y_offset: int = 0, chunk: int = 8192, mode: str = "auto") -> int:
+    """``process_level`` whose result goes straight into the exchange step: the rank's grid rows are cut into the exchange's
+    row groups, each group is enqueued (tile scan + ResNet18, survivor count on the device) and packed as one segment, then
+    ``exchange.merge()`` is enqueued.  No host wait anywhere; call ``exchange.result()`` for the merged, canonically
+    ordered, (with several ranks) all-gathered survivors.  Returns the number of candidates of this rank."""
+    H, W = int(level_img.shape[0]), int(level_img.shape[1])
+    P, S = patch_and_stride(level, stride)
+    nx, ny_all = grid_shape(W, H, S)
+    i0, i1 = (0, ny_all) if row_range is None else (int(row_range[0]), int(row_range[1]))
+    rows_per_group = max(1, exchange.cap // max(nx, 1))
+    if (i1 - i0 + rows_per_group - 1) // rows_per_group > exchange.spr:
+        raise ValueError(f"{i1 - i0} grid rows need more than the exchange's {exchange.spr} segments of {rows_per_group} rows")
+    g = 0
+    for a in range(i0, i1, rows_per_group):
+        seg = process_level_enqueue(level_img, lesion_mask, level, packed, stride=stride, row_range=(a, min(a + rows_per_group, i1)),
+                                    chunk=chunk, mode=mode)
+        exchange.pack(g, seg.pend.coords, seg.pend.labels, seg.features, seg.logits, seg.count, y_offset=y_offset)
+        g += 1
+    for e in range(g, exchange.spr):
+        exchange.pack_empty(e)
+    exchange.merge()
+    return nx * (i1 - i0)
 
 
 class HostPipeline:
@@ -173,12 +240,17 @@ def upload_group_bounds(i0: int, i1: int, groups: int):
 
 
 def process_level_host(level_img_host: torch.Tensor, mask_host, level: int, packed: _features.PackedResNet18,
-                       pipe: HostPipeline, stride=None, row_range=None, groups: int = 4, chunk: int = 8192) -> LevelResult:
+                       pipe: HostPipeline, stride=None, row_range=None, groups: int = 4, chunk: int = 8192,
+                       exchange=None, y_offset: int = 0) -> LevelResult:
     """Same as ``process_level`` for HOST inputs; returns HOST tensors (pinned views, valid until the next call).
 
     The candidate grid rows are cut into ``groups`` contiguous groups.  All uploads are queued in row order
     on the copy stream; group ``g`` is scanned as soon as the rows it touches (its own + the
-    ``patch - stride`` halo) have landed, while the rest of the image is still in flight."""
+    ``patch - stride`` halo) have landed, while the rest of the image is still in flight.
+
+    ``exchange``: a ``sharding.SurvivorExchange`` with ``segs_per_rank >= groups``.  Every group then becomes one segment
+    of the exchange step (packed on the device, no per-group host wait), the merged -- with several ranks: all-gathered --
+    canonically ordered result is what comes back to the host, with ``y_offset`` added to this rank's y coordinates."""
     H, W = int(level_img_host.shape[0]), int(level_img_host.shape[1])
     P, S = patch_and_stride(level, stride)
     nx, ny_all = grid_shape(W, H, S)
@@ -202,10 +274,33 @@ def process_level_host(level_img_host: torch.Tensor, mask_host, level: int, pack
             ev = torch.cuda.Event()
             ev.record(pipe.copy_stream)
             events.append(ev)
+    mask_dev = pipe.mask if (pipe.mask is not None and mask_host is not None) else None
+    if exchange is not None:
+        if exchange.spr < groups:
+            raise ValueError(f"exchange has {exchange.spr} segments per rank, {groups} row groups need one each")
+        n_cand = 0
+        for g in range(exchange.spr):
+            if g >= groups or bounds[g + 1] <= bounds[g]:
+                exchange.pack_empty(g)
+                continue
+            main.wait_event(events[g])
+            seg = process_level_enqueue(pipe.img, mask_dev, level, packed, stride=stride, row_range=(bounds[g], bounds[g + 1]), chunk=chunk)
+            exchange.pack(g, seg.pend.coords, seg.pend.labels, seg.features, seg.logits, seg.count, y_offset=y_offset)
+            n_cand += nx * (bounds[g + 1] - bounds[g])
+        exchange.merge()
+        res = exchange.result()
+        n = int(res["coords"].shape[0])
+        h_coords, h_labels, h_feats, h_logits = pipe.host_buffers(max(n, 1))
+        h_coords[:n].copy_(res["coords"], non_blocking=True)
+        h_labels[:n].copy_(res["labels"], non_blocking=True)
+        h_feats[:n].copy_(res["features"], non_blocking=True)
+        if "logits" in res:
+            h_logits[:n].copy_(res["logits"], non_blocking=True)
+        main.synchronize()
+        return LevelResult(h_coords[:n], h_labels[:n], h_feats[:n], h_logits[:n] if packed.num_classes > 0 else None, n_cand)
     cap = nx * (i1 - i0)
     h_coords, h_labels, h_feats, h_logits = pipe.host_buffers(cap)
     n_total, n_cand = 0, 0
-    mask_dev = pipe.mask if (pipe.mask is not None and mask_host is not None) else None
     for g in range(groups):
         if bounds[g + 1] <= bounds[g]:
             continue

@@ -12,6 +12,8 @@ from __future__ import annotations
 import torch
 import torch.distributed as dist
 
+from . import _lib
+
 
 def shard_rows(ny_total: int, world: int, rank: int):
     """Contiguous candidate grid-row range ``[i0, i1)`` of ``rank``; sizes differ by at most one row."""
@@ -96,3 +98,90 @@ def gather_survivors(tensors: dict, group=None, sort: bool = True, count_group=N
         perm = canonical_order(out["coords"])
         out = {k: v[perm] for k, v in out.items()}
     return out
+
+
+class SurvivorExchange:
+    """The exchange step on the CUDA path: fixed-size, count-free, sort-free (``csrc/exchange.cu``).
+
+    Every rank owns ``segs_per_rank`` SEGMENTS (one per tile-scan + forward pass over a contiguous range of candidate grid
+    rows, in ascending y order); ``pack`` writes a segment's capacity-sized outputs and its DEVICE-side survivor count
+    into the send buffer, ``merge`` runs ONE ``all_gather_into_tensor`` (NCCL over NVLink; the counts travel in the
+    segment headers) and the library's index + scatter kernels, which place every row at its final position in the
+    canonical ``(x, y)`` order -- array-equal to a single-rank run.  Nothing waits on the host: all of it is enqueued
+    behind the network kernels and the next step's kernels queue up behind it; ``total`` stays on the device until
+    ``result()`` is asked for.  With ``world == 1`` the same merge turns the row groups of one rank into one ordered
+    result (no collective)."""
+
+    def __init__(self, device, seg_capacity: int, num_classes: int, nx: int, stride: int, segs_per_rank: int = 1, group=None,
+                 with_features: bool = True):
+        self.device = torch.device(device)
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.cap, self.k, self.nx, self.stride, self.spr = int(seg_capacity), int(num_classes), int(nx), int(stride), int(segs_per_rank)
+        self.fd = 512 if with_features else 0
+        l = _lib.lib()
+        self.seg_bytes = int(l.hipac_exchange_segment_bytes(self.cap, self.fd, self.k))
+        self.nseg = self.world * self.spr
+        self.send = torch.empty((self.spr * self.seg_bytes,), dtype=torch.uint8, device=self.device)
+        self.recv = torch.empty((self.nseg * self.seg_bytes,), dtype=torch.uint8, device=self.device) if self.world > 1 else self.send
+        self.out_cap = self.nseg * self.cap
+        self.coords = torch.empty((max(self.out_cap, 1), 2), dtype=torch.int32, device=self.device)
+        self.labels = torch.empty((max(self.out_cap, 1),), dtype=torch.uint8, device=self.device)
+        self.features = torch.empty((max(self.out_cap, 1), 512), dtype=torch.float32, device=self.device) if self.fd else None
+        self.logits = torch.empty((max(self.out_cap, 1), max(self.k, 1)), dtype=torch.float32, device=self.device)
+        self.total = torch.zeros((2,), dtype=torch.int32, device=self.device)
+        self.ws = torch.empty((int(l.hipac_exchange_workspace_bytes(self.nseg, self.nx)),), dtype=torch.uint8, device=self.device)
+        self._total_host = torch.zeros((2,), dtype=torch.int32).pin_memory() if self.device.type == "cuda" else None
+
+    def pack(self, seg: int, coords, labels, features, logits, count: torch.Tensor, y_offset: int = 0, stream=None):
+        """Enqueue the packing of local segment ``seg``; ``count`` is the int32 device counter of the scan (element 0) and
+        the tensors hold at least ``min(count, their own first dimension)`` valid rows (at most the segment capacity)."""
+        if not (0 <= seg < self.spr):
+            raise ValueError(f"segment {seg} outside [0, {self.spr})")
+        rows = int(coords.shape[0])
+        if rows > self.cap:
+            raise ValueError(f"{rows} candidate rows exceed the segment capacity {self.cap}")
+        if (self.fd and (features is None or int(features.shape[0]) < rows)) or (self.k and (logits is None or int(logits.shape[0]) < rows)):
+            raise ValueError("feature / logit tensors are missing or shorter than the coordinate tensor")
+        st = stream or torch.cuda.current_stream(self.device)
+        dst = self.send[seg * self.seg_bytes:]
+        _lib.check(_lib.lib().hipac_exchange_pack(coords.data_ptr(), labels.data_ptr(), features.data_ptr() if self.fd else None,
+                                                  logits.data_ptr() if self.k else None, self.fd, self.k,
+                                                  count.data_ptr(), rows, int(y_offset), dst.data_ptr(), st.cuda_stream),
+                   "hipac_exchange_pack")
+
+    def pack_empty(self, seg: int, stream=None):
+        """Mark local segment ``seg`` as holding no rows (a rank with fewer row groups than ``segs_per_rank``)."""
+        if getattr(self, "_zero", None) is None:
+            self._zero = torch.zeros((2,), dtype=torch.int32, device=self.device)
+        st = stream or torch.cuda.current_stream(self.device)
+        dst = self.send[seg * self.seg_bytes:]
+        _lib.check(_lib.lib().hipac_exchange_pack(self.coords.data_ptr(), self.labels.data_ptr(), self.features.data_ptr() if self.fd else None,
+                                                  self.logits.data_ptr() if self.k else None, self.fd, self.k, self._zero.data_ptr(), 0, 0,
+                                                  dst.data_ptr(), st.cuda_stream), "hipac_exchange_pack")
+
+    def merge(self, stream=None):
+        """Enqueue the all-gather (world > 1) and the index + scatter kernels; returns nothing (see ``result``)."""
+        st = stream or torch.cuda.current_stream(self.device)
+        with torch.cuda.stream(st):
+            if self.world > 1:
+                dist.all_gather_into_tensor(self.recv, self.send, group=self.group)
+            _lib.check(_lib.lib().hipac_exchange_merge(self.recv.data_ptr(), self.nseg, self.cap, self.fd, self.k, self.stride, self.nx,
+                                                       self.coords.data_ptr(), self.labels.data_ptr(),
+                                                       self.features.data_ptr() if self.fd else None,
+                                                       self.logits.data_ptr() if self.k else None, self.total.data_ptr(), self.out_cap,
+                                                       self.ws.data_ptr(), int(self.ws.numel()), st.cuda_stream),
+                       "hipac_exchange_merge")
+
+    def result(self) -> dict:
+        """Wait for the merge and slice the outputs to the true row count (the one host read of the step)."""
+        self._total_host.copy_(self.total, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        n = min(int(self._total_host[0]), self.out_cap)
+        out = {"coords": self.coords[:n], "labels": self.labels[:n]}
+        if self.fd:
+            out["features"] = self.features[:n]
+        if self.k:
+            out["logits"] = self.logits[:n]
+        return out

@@ -6,7 +6,7 @@
     python tools/run_config.py batch   [--slides 16] [--size 8192]    # configs[4]: N slides, each tile-row-sharded over the ranks
 
 `heatmap` and `batch` shard by candidate tile-row range.  Under torch.distributed.run every rank does its share and the
-results meet in the one exchange step (sharding.gather_survivors over NCCL); without it `--ranks R --rank r` runs the share
+results meet in the one exchange step (sharding.SurvivorExchange: device-side pack + one NCCL all-gather + index/scatter kernels); without it `--ranks R --rank r` runs the share
 of rank r of R on this GPU (the "no cluster" form of the same decomposition).  Synthetic slides are generated on the host
 cores (not timed); each command prints ONE JSON line with device-timed throughput (CUDA events, max over ranks).
 """
@@ -80,12 +80,8 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    count_group = None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-        if os.environ.get("MASTER_ADDR", "127.0.0.1") in ("127.0.0.1", "localhost"):
-            os.environ.setdefault("GLOO_SOCKET_IFNAME", "lo")   # single node: do not depend on the hostname resolving
-        count_group = dist.new_group(backend="gloo")
     eff_world, eff_rank = (world, rank) if world > 1 else (args.ranks or 1, args.rank)
     threads = max(1, min(16, len(os.sched_getaffinity(0)) // world))
     torch.set_num_threads(threads)
@@ -123,26 +119,38 @@ def main():
         img_h, msk_h = host_slab(4321, level, size, size, y0, y1, threads)
         gen_s = time.perf_counter() - t0
         img, msk = img_h.to(dev), msk_h.to(dev)
+        rows_max = max(sharding.shard_rows(ny, eff_world, r)[1] - sharding.shard_rows(ny, eff_world, r)[0] for r in range(eff_world))
+        # the heatmap needs coordinates, labels and logits only: the features stay on their rank
+        xchg = pipeline.exchange_for_level(dev, size, rows_max, S, 2, with_features=False)
+
         def run():
-            r = pipeline.process_level(img, msk, level, packed, stride=S, row_range=(0, i1 - i0))
-            coords = r.coords.clone()
-            coords[:, 1] += y0
-            g = sharding.gather_survivors({"coords": coords, "labels": r.labels, "logits": r.logits}, sort=True,
-                                          count_group=count_group) if world > 1 else {"coords": coords, "labels": r.labels, "logits": r.logits}
+            n_cand = pipeline.process_level_exchanged(img, msk, level, packed, xchg, stride=S, row_range=(0, i1 - i0), y_offset=y0)
+            g = xchg.result()
             hm = heatmap.heatmap(g["coords"], g["logits"], size, size, S, fill=0.0)
-            return r, g, hm
+            return n_cand, g, hm
 
         run()   # untimed first pass (allocator warm-up)
-        ms, (r, g, hm) = timed(run)
+        ms, (n_cand, g, hm) = timed(run)
         ms = max_over_ranks(ms, dev)
         n_all = int(g["coords"].shape[0])
+        ys = g["coords"][:, 1]
+        n_mine = int(((ys >= i0 * S) & (ys < i1 * S)).sum())
+        import zlib
+        hm_np = hm.cpu().numpy()
+        crc = zlib.crc32(hm_np.tobytes())
+        # per-shard CRC of the heatmap rows: a real N-rank run prints all N, an emulated rank its own -- they must agree
+        blocks = {}
+        for r in (range(eff_world) if world > 1 else [eff_rank]):
+            a, b = sharding.shard_rows(ny, eff_world, r)
+            blocks[str(r)] = f"{zlib.crc32(np.ascontiguousarray(hm_np[a:b]).tobytes()):08x}"
         if args.csv and rank == 0:
             heatmap.write_froc_csv(args.csv, g["coords"], g["logits"], level, P, threshold=0.5)
         out.update({"slide": f"{size}x{size} level image, P=S=224", "grid": [int(hm.shape[0]), int(hm.shape[1])],
-                    "rows_of_this_rank": [i0, i1], "candidates_this_rank": r.candidates, "survivors_this_rank": len(r),
+                    "rows_of_this_rank": [i0, i1], "candidates_this_rank": n_cand, "survivors_this_rank": n_mine,
                     "survivors_gathered": n_all, "tumor_labelled": int(g["labels"].sum()), "ms": round(ms, 2),
-                    "patches_per_s_this_rank" if world == 1 else "patches_per_s": round((len(r) if world == 1 else n_all) / (ms * 1e-3), 1),
-                    "candidates_per_s_this_rank": round(r.candidates / (ms * 1e-3), 1), "heatmap_sum": float(hm.sum()),
+                    "patches_per_s_this_rank" if world == 1 else "patches_per_s": round((n_mine if world == 1 else n_all) / (ms * 1e-3), 1),
+                    "candidates_per_s_this_rank": round(n_cand / (ms * 1e-3), 1), "heatmap_sum": float(hm.double().sum()),
+                    "heatmap_crc32": f"{crc:08x}", "heatmap_block_crc32": blocks, "segments": xchg.nseg, "exchange_bytes_per_rank": int(xchg.send.numel()),
                     "host_generation_s": round(gen_s, 1)})
 
     else:
@@ -158,23 +166,38 @@ def main():
         slabs = [host_slab(1000 + s, L, w, h, y0, y1, threads) for s in range(args.slides)]
         gen_s = time.perf_counter() - t0
         dslabs = [(i.to(dev), m.to(dev)) for i, m in slabs]
+        rows_max = max(sharding.shard_rows(ny, eff_world, r)[1] - sharding.shard_rows(ny, eff_world, r)[0] for r in range(eff_world))
+        # one exchange object per slide in flight (two alternate): slide s+1 is enqueued while the result of slide s is read
+        xs = [pipeline.exchange_for_level(dev, w, rows_max, S, 2) for _ in range(2)]
+        import zlib
+
         def run():
-            tot, mine = 0, 0
-            for img, msk in dslabs:
-                r = pipeline.process_level(img, msk, L, packed, row_range=(0, i1 - i0))
-                coords = r.coords.clone()
-                coords[:, 1] += y0
-                t = {"coords": coords, "labels": r.labels, "features": r.features}
-                g = sharding.gather_survivors(t, sort=True, count_group=count_group) if world > 1 else t
-                tot += int(g["coords"].shape[0])
-                mine += len(r)
-            return tot, mine
+            tot, mine, crc = 0, 0, 0
+            pending = None
+            for s, (img, msk) in enumerate(dslabs):
+                x = xs[s & 1]
+                pipeline.process_level_exchanged(img, msk, L, packed, x, row_range=(0, i1 - i0), y_offset=y0)
+                if pending is not None:
+                    g = pending.result()
+                    tot += int(g["coords"].shape[0])
+                    ys = g["coords"][:, 1]
+                    mine += int(((ys >= i0 * S) & (ys < i1 * S)).sum())
+                pending = x
+            g = pending.result()
+            tot += int(g["coords"].shape[0])
+            ys = g["coords"][:, 1]
+            mine += int(((ys >= i0 * S) & (ys < i1 * S)).sum())
+            return tot, mine, g
 
         run()   # untimed first pass (allocator warm-up)
-        ms, (tot, mine) = timed(run)
+        ms, (tot, mine, g_last) = timed(run)
         ms = max_over_ranks(ms, dev)
+        crc = 0
+        for k in ("coords", "labels", "features", "logits"):
+            crc = zlib.crc32(g_last[k].cpu().numpy().tobytes(), crc)
         out.update({"slides": args.slides, "slide": f"{w}x{h} level-{L} image, P={P}, S={S}", "rows_of_this_rank": [i0, i1],
                     "survivors_gathered": tot, "survivors_this_rank": mine, "ms": round(ms, 2),
+                    "last_slide_patch_set_crc32": f"{crc:08x}",
                     "patches_per_s": round((tot if world > 1 else mine) / (ms * 1e-3), 1), "host_generation_s": round(gen_s, 1)})
 
     if rank == 0:
