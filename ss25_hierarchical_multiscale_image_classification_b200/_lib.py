@@ -37,12 +37,23 @@ def _nvcc() -> str:
     return "nvcc"
 
 
+def _source_hash() -> str:
+    """sha256 over the CUDA sources and the public header: what a built library is a function of."""
+    import hashlib
+    h = hashlib.sha256()
+    for d in sorted(os.path.join(_CSRC, f) for f in os.listdir(_CSRC)) + [HEADER]:
+        h.update(os.path.basename(d).encode())
+        h.update(open(d, "rb").read())
+    return h.hexdigest()
+
+
 def _stale(path: str = LIB_PATH) -> bool:
-    if not os.path.exists(path):
+    """A library is fresh iff the source hash recorded beside it equals the current one (file times do not survive the
+    copy to the GPU box, so they are not consulted)."""
+    try:
+        return open(path + ".srchash").read().strip() != _source_hash() or not os.path.exists(path)
+    except OSError:
         return True
-    t = os.path.getmtime(path)
-    deps = [os.path.join(_CSRC, f) for f in os.listdir(_CSRC)] + [HEADER]
-    return any(os.path.getmtime(d) > t for d in deps)
 
 
 def build(force: bool = False, verbose: bool = False, debug_bounds: bool = False) -> str:
@@ -51,6 +62,20 @@ def build(force: bool = False, verbose: bool = False, debug_bounds: bool = False
     out_path = DBG_LIB_PATH if debug_bounds else LIB_PATH
     if not force and not _stale(out_path):
         return out_path
+    # several ranks may call build() at once (torchrun): one compiles, the others wait and find a fresh library
+    import fcntl
+    with open(os.path.join(_HERE, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not _stale(out_path):
+                return out_path
+            return _build_locked(out_path, verbose, debug_bounds)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(out_path: str, verbose: bool, debug_bounds: bool) -> str:
+    src_hash = _source_hash()
     objs = []
     build_dir = os.path.join(_HERE, "build", "dbg" if debug_bounds else "")
     os.makedirs(build_dir, exist_ok=True)
@@ -76,6 +101,8 @@ def build(force: bool = False, verbose: bool = False, debug_bounds: bool = False
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}")
     os.replace(out_path + ".tmp", out_path)
+    with open(out_path + ".srchash", "w") as f:
+        f.write(src_hash + "\n")
     return out_path
 
 

@@ -46,7 +46,11 @@ def test_two_ranks_equal_one_rank_bitwise(level):
            "--master-port", str(port), os.path.join(ROOT, "tools", "check_sharded.py"), "--level", str(level),
            "--width", "5000" if level == 1 else "3000", "--rows-per-rank", "2300" if level == 1 else "1300"]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT)
-    assert r.returncode == 0, (r.stdout[-2000:], r.stderr[-4000:])
+    out_dir = os.path.join(ROOT, "gpurun_out")
+    if os.path.isdir(out_dir):
+        open(os.path.join(out_dir, f"check_sharded_l{level}.log"), "w").write(r.stdout + "\n---- stderr ----\n" + r.stderr)
+    err = "\n".join(l for l in r.stderr.splitlines() if "Error" in l or "error" in l or "Traceback" in l or "  File" in l)
+    assert r.returncode == 0, (r.stdout[-1500:], err[-3000:])
     rec = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
     assert rec["equals_single_rank"] and rec["all_ranks_hold_identical_bytes"] and rec["world"] == 2
     assert rec["survivors_gathered"] == rec["survivors_single_rank"] > 0
