@@ -264,6 +264,7 @@ k_conv_umma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 }
 
 #include "conv_rows.cuh"
+#include "conv_rows2.cuh"
 #include "conv_stem.cuh"
 
 // ==========================================================================================
@@ -372,6 +373,8 @@ static thread_local int g_num_sms = 0;   // SM count of the CURRENT device, refr
 static bool g_use_fused_stem = true;   // HIPAC_FUSED_STEM=0 runs conv1 and the max pool as two kernels
 static bool g_fuse_downsample = true; // HIPAC_FUSE_DS=0 runs the 1x1 projection shortcuts as separate kernels
 static bool g_use_row_kernels = true;  // HIPAC_CONV_ROWS=0 forces the im2col kernel everywhere (A/B comparison)
+static bool g_use_cta_pairs = true;    // HIPAC_CTA_PAIRS=0: single-CTA row kernels instead of the cta_group::2 ones
+static bool g_use_cta_pairs_c64 = false;   // HIPAC_CTA_PAIRS_C64=1: CTA pairs for the 64-channel layers too (measured slower)
 
 // A/B switches for measurements; read once (the workspace size depends on them).
 static bool g_boustrophedon = true;   // alternate the tile order from layer to layer (A/B switch: HIPAC_BOUSTROPHEDON=0)
@@ -379,6 +382,8 @@ static void read_env_flags() {
   static std::once_flag once;
   std::call_once(once, [] {
     if (const char* e = getenv("HIPAC_CONV_ROWS")) g_use_row_kernels = atoi(e) != 0;
+    if (const char* e = getenv("HIPAC_CTA_PAIRS")) g_use_cta_pairs = atoi(e) != 0;
+    if (const char* e = getenv("HIPAC_CTA_PAIRS_C64")) g_use_cta_pairs_c64 = atoi(e) != 0;
     if (const char* e = getenv("HIPAC_FUSED_STEM")) g_use_fused_stem = atoi(e) != 0;
     if (const char* e = getenv("HIPAC_FUSE_DS")) g_fuse_downsample = atoi(e) != 0;
     if (const char* e = getenv("HIPAC_BOUSTROPHEDON")) g_boustrophedon = atoi(e) != 0;
@@ -491,6 +496,63 @@ static int launch_rows_t(const uint8_t* d_packed, const PackedLayout& L, int lay
   return 0;
 }
 
+// NHWC activation tensor as a strided tiled map for the fused 1x1 / stride-2 projection: the box spans 2*wp x 2*r input
+// pixels with element strides 2, i.e. delivers wp x r pixels x 64 channels (out-of-range pixels zero filled).
+static int make_strided_map(CUtensorMap* map, const void* ptr, int n, int h, int w, int c, int wp, int r) {
+  cuuint64_t dims[4] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
+  cuuint64_t strides[3] = {(cuuint64_t)c * 2, (cuuint64_t)w * c * 2, (cuuint64_t)h * w * c * 2};
+  cuuint32_t box[4] = {64, (cuuint32_t)(2 * wp), (cuuint32_t)(2 * r), 1};
+  cuuint32_t estr[4] = {1, 2, 2, 1};
+  CUresult res = g_encode_tiled(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (res != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (strided projection map) failed with CUresult " + std::to_string((int)res));
+    return -5;
+  }
+  return 0;
+}
+
+// CTA-pair row kernel (conv_rows2.cuh).  weights = [BN][9*KC*64 (+ KDS*64)] K-major at w_ptr; ds_in = block input of the
+// fused projection shortcut (KDS = 1) or null.
+template <int BN, int KC, int W, int R, int KDS>
+static int launch_rows2_t(const void* w_ptr, const float* bias, const void* in, const void* ds_in, const void* residual, void* out,
+                          int n, bool relu, cudaStream_t stream, const char* name, double flops) {
+  using Cfg = Row2Cfg<BN, KC, W, R, KDS>;
+  if (int e = ensure_dyn_smem(k_conv3x3_rows2<BN, KC, W, R, KDS>, Cfg::kSmemBytes)) return e;
+  CUtensorMap tmA, tmB, tmA2;
+  if (int e = make_region_map(&tmA, in, n, W, W, KC * 64, R)) return e;
+  if (int e = make_weight_map(&tmB, w_ptr, BN, (9 * KC + KDS) * 64, BN / 2)) return e;
+  if (KDS) {
+    if (int e = make_strided_map(&tmA2, ds_in, n, 2 * W, 2 * W, 64, W + 2, R)) return e;
+  } else {
+    tmA2 = tmA;
+  }
+  RowConvParams p;
+  p.n_img = n, p.num_tiles = n * (W / R), p.relu = relu ? 1 : 0;
+  p.n_dev = g_n_dev, p.n_base = g_n_base, p.reverse = g_reverse;
+  p.bias = bias;
+  p.residual = reinterpret_cast<const __nv_bfloat16*>(residual);
+  p.out = reinterpret_cast<__nv_bfloat16*>(out);
+  const int pairs = (p.num_tiles + 1) / 2;
+  const int max_pairs = g_num_sms / 2;
+  const int grid = 2 * (pairs < max_pairs ? pairs : max_pairs);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid), cfg.blockDim = dim3((unsigned)conv_threads(BN));
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes, cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr, cfg.numAttrs = 1;
+  {
+    ProfileScope ps(name, stream, flops);
+    HIPAC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, k_conv3x3_rows2<BN, KC, W, R, KDS>, tmA, tmB, tmA2, p));
+  }
+  count_launch(1);
+  HIPAC_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
 // Fused conv1 + BN + ReLU + maxpool on the S2D16 batch -> [n][56][56][64].
 static int run_stem(const uint8_t* d_packed, const PackedLayout& L, const void* in, void* out, int n, cudaStream_t stream) {
   if (int e = ensure_dyn_smem(k_conv1_pool, kStemSmem)) return e;
@@ -546,10 +608,19 @@ static int run_conv(const uint8_t* d_packed, const PackedLayout& L, int layer, c
   const ConvSpec& cs = kConvs[layer];
   const int K = conv_gemm_k(layer);
   if (g_use_row_kernels && cs.k == 3 && cs.stride == 1) {
-    if (cs.cin == 64 && cs.hin == 56)
+    const float* bias = reinterpret_cast<const float*>(d_packed + L.b_off[layer]);
+    if (cs.cin == 64 && cs.hin == 56) {
+      if (g_use_cta_pairs && g_use_cta_pairs_c64)
+        return launch_rows2_t<64, 1, 56, 2, 0>(d_packed + L.w_off[layer], bias, in, nullptr, residual, out, n, relu, stream, "conv3x3_c64",
+                                               2.0 * n * 56 * 56 * 64 * 576);
       return launch_rows_t<64, 1, 56, 2, true>(d_packed, L, layer, in, residual, out, n, relu, stream, "conv3x3_c64");
-    if (cs.cin == 128 && cs.hin == 28)
+    }
+    if (cs.cin == 128 && cs.hin == 28) {
+      if (g_use_cta_pairs)
+        return launch_rows2_t<128, 2, 28, 4, 0>(d_packed + L.w_off[layer], bias, in, nullptr, residual, out, n, relu, stream, "conv3x3_c128",
+                                                2.0 * n * 28 * 28 * 128 * 1152);
       return launch_rows_t<128, 2, 28, 4, false>(d_packed, L, layer, in, residual, out, n, relu, stream, "conv3x3_c128");
+    }
   }
   ConvParams p;
   p.M_total = n * cs.hout * cs.hout;
@@ -595,6 +666,11 @@ static int run_conv_ds_fused(const uint8_t* d_packed, const PackedLayout& L, int
                              int n, cudaStream_t stream) {
   const int lc = fused_conv_layer(s), ld = fused_ds_layer(s);
   const ConvSpec &cs = kConvs[lc], &ds = kConvs[ld];
+  if (s == 0 && g_use_row_kernels && g_use_cta_pairs) {
+    // layer2.0: 3x3 128 -> 128 at 28x28 + 1x1/s2 64 -> 128 from the 56x56 block input, on CTA pairs with resident weights
+    return launch_rows2_t<128, 2, 28, 4, 1>(d_packed + L.wf_off[0], reinterpret_cast<const float*>(d_packed + L.bf_off[0]), in, block_in,
+                                            nullptr, out, n, true, stream, "conv3x3+ds_c128", 2.0 * n * 28 * 28 * 128 * fused_gemm_k(0));
+  }
   ConvParams p;
   p.M_total = n * cs.hout * cs.hout;
   p.hw_out = cs.hout * cs.hout, p.wout = cs.hout;
