@@ -30,9 +30,7 @@ struct StemParams {
   int reverse;         // block order, see g_reverse
 };
 
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
+using ptx::named_bar_sync;
 
 __device__ __forceinline__ uint4 bf16x8_max(uint4 a, uint4 b) {
   uint4 r;

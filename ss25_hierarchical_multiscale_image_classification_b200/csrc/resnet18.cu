@@ -265,6 +265,7 @@ k_conv_umma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
 #include "conv_rows.cuh"
 #include "conv_rows2.cuh"
+#include "conv_rows_tma.cuh"
 #include "conv_stem.cuh"
 
 // ==========================================================================================
@@ -374,6 +375,7 @@ static bool g_use_fused_stem = true;   // HIPAC_FUSED_STEM=0 runs conv1 and the 
 static bool g_fuse_downsample = true; // HIPAC_FUSE_DS=0 runs the 1x1 projection shortcuts as separate kernels
 static bool g_use_row_kernels = true;  // HIPAC_CONV_ROWS=0 forces the im2col kernel everywhere (A/B comparison)
 static bool g_use_cta_pairs = true;    // HIPAC_CTA_PAIRS=0: single-CTA row kernels instead of the cta_group::2 ones
+static bool g_tma_epilogue = true;     // HIPAC_TMA_EPILOGUE=0: 64-channel layers store / fetch the residual per thread (k_conv3x3_rows)
 static bool g_use_cta_pairs_c64 = false;   // HIPAC_CTA_PAIRS_C64=1: CTA pairs for the 64-channel layers too (measured slower)
 
 // A/B switches for measurements; read once (the workspace size depends on them).
@@ -384,6 +386,7 @@ static void read_env_flags() {
     if (const char* e = getenv("HIPAC_CONV_ROWS")) g_use_row_kernels = atoi(e) != 0;
     if (const char* e = getenv("HIPAC_CTA_PAIRS")) g_use_cta_pairs = atoi(e) != 0;
     if (const char* e = getenv("HIPAC_CTA_PAIRS_C64")) g_use_cta_pairs_c64 = atoi(e) != 0;
+    if (const char* e = getenv("HIPAC_TMA_EPILOGUE")) g_tma_epilogue = atoi(e) != 0;
     if (const char* e = getenv("HIPAC_FUSED_STEM")) g_use_fused_stem = atoi(e) != 0;
     if (const char* e = getenv("HIPAC_FUSE_DS")) g_fuse_downsample = atoi(e) != 0;
     if (const char* e = getenv("HIPAC_BOUSTROPHEDON")) g_boustrophedon = atoi(e) != 0;
@@ -513,6 +516,54 @@ static int make_strided_map(CUtensorMap* map, const void* ptr, int n, int h, int
   return 0;
 }
 
+// NHWC activation tensor as a tiled map whose box is one OUTPUT row tile: 64 channels x w x r x 1 (TMA store of the
+// epilogue's staging tile / TMA load of the residual tile).
+static int make_tile_map(CUtensorMap* map, const void* ptr, int n, int h, int w, int c, int r) {
+  cuuint64_t dims[4] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
+  cuuint64_t strides[3] = {(cuuint64_t)c * 2, (cuuint64_t)w * c * 2, (cuuint64_t)h * w * c * 2};
+  cuuint32_t box[4] = {64, (cuuint32_t)w, (cuuint32_t)r, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult res = g_encode_tiled(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (res != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (tile map) failed with CUresult " + std::to_string((int)res));
+    return -5;
+  }
+  return 0;
+}
+
+// 64-channel row kernel with the TMA epilogue (conv_rows_tma.cuh).
+template <int KC, int W, int R>
+static int launch_rows_tma_t(const uint8_t* d_packed, const PackedLayout& L, int layer, const void* in, const void* residual, void* out,
+                             int n, bool relu, cudaStream_t stream, const char* name) {
+  using Cfg = RowTmaCfg<KC, W, R>;
+  if (int e = ensure_dyn_smem(k_conv3x3_rows_tma<KC, W, R>, Cfg::kSmemBytes)) return e;
+  CUtensorMap tmA, tmB, tmO, tmR;
+  if (int e = make_region_map(&tmA, in, n, W, W, KC * 64, R)) return e;
+  if (int e = make_weight_map(&tmB, d_packed + L.w_off[layer], 64, 9 * KC * 64, 64)) return e;
+  if (int e = make_tile_map(&tmO, out, n, W, W, 64, R)) return e;
+  if (residual) {
+    if (int e = make_tile_map(&tmR, residual, n, W, W, 64, R)) return e;
+  } else {
+    tmR = tmO;
+  }
+  RowConvParams p;
+  p.n_img = n, p.num_tiles = n * (W / R), p.relu = relu ? 1 : 0;
+  p.n_dev = g_n_dev, p.n_base = g_n_base, p.reverse = g_reverse;
+  p.bias = reinterpret_cast<const float*>(d_packed + L.b_off[layer]);
+  p.residual = reinterpret_cast<const __nv_bfloat16*>(residual);
+  p.out = reinterpret_cast<__nv_bfloat16*>(out);
+  const int grid = p.num_tiles < g_num_sms ? p.num_tiles : g_num_sms;
+  {
+    ProfileScope ps(name, stream, 2.0 * n * W * W * 64 * 9 * KC * 64);
+    k_conv3x3_rows_tma<KC, W, R><<<grid, conv_threads(64), Cfg::kSmemBytes, stream>>>(tmA, tmB, tmO, tmR, p);
+  }
+  count_launch(1);
+  HIPAC_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
 // CTA-pair row kernel (conv_rows2.cuh).  weights = [BN][9*KC*64 (+ KDS*64)] K-major at w_ptr; ds_in = block input of the
 // fused projection shortcut (KDS = 1) or null.
 template <int BN, int KC, int W, int R, int KDS>
@@ -613,6 +664,7 @@ static int run_conv(const uint8_t* d_packed, const PackedLayout& L, int layer, c
       if (g_use_cta_pairs && g_use_cta_pairs_c64)
         return launch_rows2_t<64, 1, 56, 2, 0>(d_packed + L.w_off[layer], bias, in, nullptr, residual, out, n, relu, stream, "conv3x3_c64",
                                                2.0 * n * 56 * 56 * 64 * 576);
+      if (g_tma_epilogue) return launch_rows_tma_t<1, 56, 2>(d_packed, L, layer, in, residual, out, n, relu, stream, "conv3x3_c64");
       return launch_rows_t<64, 1, 56, 2, true>(d_packed, L, layer, in, residual, out, n, relu, stream, "conv3x3_c64");
     }
     if (cs.cin == 128 && cs.hin == 28) {
