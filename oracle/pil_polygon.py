@@ -122,7 +122,7 @@ def fill_polygon(img: np.ndarray, xy, ink: int = 255):
                 xx.append(_x_at(cur, y))
                 if y == cur.ymax and y < ymax:
                     xx.append(xx[-1])
-                elif cur.dx != 0 and len(xx) % 2 == 1 and _is_int_roundf(xx[-1]):
+                elif cur.dx != 0 and len(xx) % 2 == 0 and _is_int_roundf(xx[-1]):
                     for k in range(i):
                         other = table[k]
                         if (cur.dx > 0 and other.dx <= 0) or (cur.dx < 0 and other.dx >= 0):

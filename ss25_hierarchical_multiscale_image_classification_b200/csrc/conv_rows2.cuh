@@ -30,9 +30,15 @@ struct Row2Cfg {
   static constexpr int kBBlock = kBHalf * 128;              // one (tap, 64-channel slice) block of this CTA's half
   static constexpr int kNumB = 9 * KC + KDS;
   static constexpr int kBBytes = kNumB * kBBlock;
-  static constexpr int kAStages = (232448 - 1024 - 512 - kBBytes) / kRegionBytes >= 4 ? 4 : (232448 - 1024 - 512 - kBBytes) / kRegionBytes;
+  // 64-channel tiles leave through shared-memory staging + TMA (see conv_rows_tma.cuh): [warpgroup][buffer] tiles of R x W x 128 B
+  static constexpr bool kTmaEpi = BN == 64;
+  static constexpr int kTileBytes = R * W * 128;
+  static constexpr int kStageBytes = (kTileBytes + 1023) / 1024 * 1024;
+  static constexpr int kStagingBytes = kTmaEpi ? 4 * kStageBytes : 0;
+  static constexpr int kFree = 232448 - 1024 - 512 - kBBytes - kStagingBytes;
+  static constexpr int kAStages = kFree / kRegionBytes >= 4 ? 4 : kFree / kRegionBytes;
   static constexpr int kTmemCols = 2 * BN;
-  static constexpr int kSmemBytes = kAStages * kRegionBytes + kBBytes + 1024 + 512;
+  static constexpr int kSmemBytes = kAStages * kRegionBytes + kBBytes + kStagingBytes + 1024 + 512;
   static_assert(R * Wp <= 128, "tile does not fit one UMMA M = 128 per CTA");
   static_assert(kAStages >= 2, "need at least two region stages");
   static_assert(kSmemBytes <= 232448, "shared memory budget");
@@ -41,19 +47,22 @@ struct Row2Cfg {
 template <int BN, int KC, int W, int R, int KDS>
 __global__ void __launch_bounds__(conv_threads(BN), 1)
 k_conv3x3_rows2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                const __grid_constant__ CUtensorMap tmA2, const RowConvParams p) {
+                const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmO,
+                const __grid_constant__ CUtensorMap tmR, const RowConvParams p) {
   using Cfg = Row2Cfg<BN, KC, W, R, KDS>;
   constexpr int Wp = Cfg::Wp, H = W, TILES_PER_IMG = H / R, NS = Cfg::kAStages, SLICES = KC + KDS;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = base;
   uint8_t* sB = base + NS * Cfg::kRegionBytes;
-  uint64_t* a_full = reinterpret_cast<uint64_t*>(sB + Cfg::kBBytes);   // used in the leader
+  uint8_t* sO = sB + Cfg::kBBytes;                                      // staging tiles (64-channel variant only)
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(sO + Cfg::kStagingBytes);   // used in the leader
   uint64_t* a_empty = a_full + 4;                                       // local in each CTA
   uint64_t* b_full = a_empty + 4;                                       // leader
   uint64_t* tfull = b_full + 1;                                         // local
   uint64_t* tempty = tfull + 2;                                         // leader
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint64_t* st_ready = tempty + 2;                                      // local, [warpgroup][buffer]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(st_ready + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = ptx::cluster_ctarank();
@@ -65,6 +74,11 @@ k_conv3x3_rows2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     for (int s = 0; s < NS; s++) ptx::mbar_init(&a_full[s], 2), ptx::mbar_init(&a_empty[s], 1);
     ptx::mbar_init(b_full, 2);
     for (int a = 0; a < 2; a++) ptx::mbar_init(&tfull[a], 1), ptx::mbar_init(&tempty[a], 8);
+    for (int s = 0; s < 4; s++) ptx::mbar_init(&st_ready[s], 1);
+    if (Cfg::kTmaEpi) {
+      ptx::prefetch_tensormap(&tmO);
+      if (p.residual) ptx::prefetch_tensormap(&tmR);
+    }
     ptx::fence_barrier_init();
   }
   if (warp == 1) {
@@ -156,6 +170,78 @@ k_conv3x3_rows2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         if (acc == 0) acc_phase ^= 1;
       }
     }
+  } else if constexpr (Cfg::kTmaEpi) {
+    // ===================== epilogue, 64 channels: TMEM -> staging tile (residual in place) -> TMA store =====================
+    // (same protocol as k_conv3x3_rows_tma; the accumulator-drained arrive goes to the LEADER's tempty barrier)
+    const int wq = warp & 3;
+    const int grp = (warp - 2) >> 2;
+    const int gt = threadIdx.x - 64 - 128 * grp;
+    const int pos = wq * 32 + lane;
+    const int rr = pos / Wp, x = pos - rr * Wp;
+    const bool in_tile = rr < R && x < W;
+    const int srow = rr * W + x;
+    const bool has_res = p.residual != nullptr;
+    uint8_t* stage0 = sO + grp * 2 * Cfg::kStageBytes;
+    uint64_t* ready = st_ready + grp * 2;
+    const int first = pair0 + grp * pair_step, step = 2 * pair_step;
+    auto prepare = [&](int tp, int b) {
+      bool active;
+      const int vt = tile_of(tp, active);
+      if (has_res && active) {
+        const int img = vt / TILES_PER_IMG, p0 = (vt - img * TILES_PER_IMG) * R;
+        ptx::mbar_arrive_expect_tx(&ready[b], Cfg::kTileBytes);
+        ptx::tma_load_4d(stage0 + b * Cfg::kStageBytes, &tmR, &ready[b], 0, 0, p0, img);
+      } else {
+        ptx::mbar_arrive(&ready[b]);
+      }
+    };
+    if (gt == 0 && first < num_pairs) prepare(first, 0);
+    int j = 0;
+    for (int tp = first; tp < num_pairs; tp += step, ++j) {
+      const int b = j & 1;
+      const uint32_t acc = grp, acc_phase = j & 1;
+      bool active;
+      const int vt = tile_of(tp, active);
+      uint8_t* buf = stage0 + b * Cfg::kStageBytes;
+      ptx::mbar_wait(&ready[b], (j >> 1) & 1);
+      ptx::mbar_wait(&tfull[acc], acc_phase);
+      ptx::tc_fence_after();
+      uint32_t v0[32], v1[32];
+      const uint32_t trow = tmem_base + ((uint32_t)(wq * 32) << 16) + acc * BN;
+      ptx::tmem_ld_32x32b_x32(trow, v0);
+      ptx::tmem_ld_32x32b_x32(trow + 32, v1);
+      ptx::tmem_ld_wait();
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (leader) ptx::mbar_arrive(&tempty[acc]);
+        else ptx::mbar_arrive_cluster(&tempty[acc], 0);
+      }
+      if (in_tile && active) {
+        uint4* row = reinterpret_cast<uint4*>(buf + srow * 128);
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+          const int ph = i ^ (srow & 7);
+          uint4 res = make_uint4(0u, 0u, 0u, 0u);
+          if (has_res) res = row[ph];
+          row[ph] = epilogue_chunk8(i < 4 ? &v0[8 * i] : &v1[8 * (i - 4)], p.bias + 8 * i, res, has_res, p.relu);
+        }
+      }
+      ptx::fence_proxy_async();
+      ptx::named_bar_sync(1 + grp, 128);
+      if (gt == 0) {
+        if (active) {
+          const int img = vt / TILES_PER_IMG, p0 = (vt - img * TILES_PER_IMG) * R;
+          ptx::tma_store_4d(&tmO, buf, 0, 0, p0, img);
+        }
+        ptx::bulk_commit_group();                        // (possibly empty) group: keeps the wait_group arithmetic uniform
+        if (tp + step < num_pairs) {
+          ptx::bulk_wait_group_read<1>();
+          prepare(tp + step, b ^ 1);
+        }
+      }
+    }
+    if (gt == 0) ptx::bulk_wait_group<0>();
   } else {
     // ===================== epilogue (both CTAs, own 128 accumulator rows) =====================
     const int wq = warp & 3;

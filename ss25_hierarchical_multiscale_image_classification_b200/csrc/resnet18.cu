@@ -264,8 +264,8 @@ k_conv_umma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 }
 
 #include "conv_rows.cuh"
-#include "conv_rows2.cuh"
 #include "conv_rows_tma.cuh"
+#include "conv_rows2.cuh"
 #include "conv_stem.cuh"
 
 // ==========================================================================================
@@ -579,6 +579,13 @@ static int launch_rows2_t(const void* w_ptr, const float* bias, const void* in, 
   } else {
     tmA2 = tmA;
   }
+  CUtensorMap tmO = tmA, tmR = tmA;
+  if (Cfg::kTmaEpi) {
+    if (int e = make_tile_map(&tmO, out, n, W, W, 64, R)) return e;
+    tmR = tmO;
+    if (residual)
+      if (int e = make_tile_map(&tmR, residual, n, W, W, 64, R)) return e;
+  }
   RowConvParams p;
   p.n_img = n, p.num_tiles = n * (W / R), p.relu = relu ? 1 : 0;
   p.n_dev = g_n_dev, p.n_base = g_n_base, p.reverse = g_reverse;
@@ -597,7 +604,7 @@ static int launch_rows2_t(const void* w_ptr, const float* bias, const void* in, 
   cfg.attrs = attr, cfg.numAttrs = 1;
   {
     ProfileScope ps(name, stream, flops);
-    HIPAC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, k_conv3x3_rows2<BN, KC, W, R, KDS>, tmA, tmB, tmA2, p));
+    HIPAC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, k_conv3x3_rows2<BN, KC, W, R, KDS>, tmA, tmB, tmA2, tmO, tmR, p));
   }
   count_launch(1);
   HIPAC_CHECK_CUDA(cudaGetLastError());
