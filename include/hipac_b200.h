@@ -95,6 +95,26 @@ int hipac_tile_scan_wait_count(void);
 int hipac_upload_rows(void* d_dst, int64_t dst_pitch, const void* h_src, int64_t src_pitch, int64_t row_bytes, int64_t rows,
                       void* stream);
 
+/* ---------------------------------------------------------------------------------------
+ * Lesion-mask rasterisation on the device: replaces the Pillow call inside parse_xml_mask
+ * (reference src/main.py:388-409: ImageDraw.polygon(coords, outline=255, fill=255) on an "L" image of the level size, one
+ * call per annotation), bit-exact against Pillow 12.2.0's polygon fill.  The vertices are the reference's
+ * (int(X * level_w / w0), int(Y * level_h / h0)) pairs, computed by the caller.
+ *   h_xy / h_offsets  HOST arrays: int32 [total][2] vertices of all polygons back to back, int32 [num_polygons + 1] offsets
+ *   d_xy              the same vertices in device memory (8-byte aligned)
+ *   H, W              size of the level image the vertices refer to (Pillow clamps the scan range to it)
+ *   y_begin, n_rows   the row window [y_begin, y_begin + n_rows) of that image which is rasterised (a slab of the level)
+ *   d_mask            uint8 [n_rows][pitch], row 0 = level row y_begin; every covered pixel becomes 255; `clear` zeroes the
+ *                     n_rows x W window first
+ *   d_workspace       >= hipac_polygon_workspace_bytes() bytes; holds the overflow flag read by hipac_polygon_overflowed
+ *                     (1 if some scan line crossed more than 1024 edges: the mask is then incomplete)
+ * Asynchronous on `stream` (hipac_polygon_overflowed synchronises it). */
+size_t hipac_polygon_workspace_bytes(int num_polygons);
+int hipac_polygon_fill(const int32_t* h_xy, const int32_t* h_offsets, int num_polygons, const int32_t* d_xy, uint8_t* d_mask,
+                       int H, int W, int64_t pitch, int y_begin, int n_rows, int clear, void* d_workspace, size_t workspace_bytes,
+                       void* stream);
+int hipac_polygon_overflowed(const void* d_workspace, void* stream);
+
 /* Pillow coefficient tables used by the kernels (known-answer hook for the CPU tests; no GPU needed).
  * scale in {2,4,8}; writes interior[2*scale], left_edge[3*scale/2], right_edge[3*scale/2] (22-bit fixed point). */
 int hipac_pillow_coeffs(int scale, int32_t* h_interior, int32_t* h_left, int32_t* h_right);

@@ -91,14 +91,28 @@ def _hline(img, x0, y, x1, ink):
             img[y, x0:x1 + 1] = ink
 
 
+def _roundf(v) -> np.float32:
+    """C ``roundf``: half away from zero."""
+    v = float(v)
+    return F32(math.floor(v + 0.5) if v >= 0 else -math.floor(-v + 0.5))
+
+
 def fill_polygon(img: np.ndarray, xy, ink: int = 255):
-    """``polygon_generic`` on a uint8 ``[H, W]`` array, in place."""
+    """``polygon_generic`` (Pillow 12.2.0, 8-bit path) on a uint8 ``[H, W]`` array, in place.
+
+    Read back from the installed binary (``PIL/_imaging*.so``, ``polygon_generic``), since the C source is not in the
+    container: per scan line, every non-horizontal edge active on the row contributes ``(y - y0) * dx + x0`` (float32
+    multiply then add).  An edge ENDING on the row (and the row is not the polygon's last) contributes it twice.  An edge
+    with a VERTEX on the row (its first row, or its last row on the polygon's last row) looks for an EARLIER edge that has
+    a vertex at the same rounded x on this row and is active on the adjacent row (next row; previous row for an ending
+    edge): if this corner lies more than one pixel beyond BOTH edges' positions on the adjacent row, the intersection is
+    pulled to ``roundf(max) + 1`` / ``roundf(min) - 1`` so that the corner stays 8-connected to the adjacent row's span.
+    Pairs of the sorted list are filled from ``ROUND_UP`` to ``ROUND_DOWN`` (no running clamp on the 8-bit path)."""
     if len(xy) <= 0:
         return
     h, w = img.shape
     e = build_edges(xy)
-    n = len(e)
-    if n <= 0:
+    if len(e) <= 0:
         return
     table = []
     ymin, ymax = h - 1, 0
@@ -118,45 +132,36 @@ def fill_polygon(img: np.ndarray, xy, ink: int = 255):
     for y in range(ymin, ymax + 1):
         xx = []
         for i, cur in enumerate(table):
-            if cur.ymin <= y <= cur.ymax:
-                xx.append(_x_at(cur, y))
-                if y == cur.ymax and y < ymax:
-                    xx.append(xx[-1])
-                elif cur.dx != 0 and len(xx) % 2 == 0 and _is_int_roundf(xx[-1]):
-                    for k in range(i):
-                        other = table[k]
-                        if (cur.dx > 0 and other.dx <= 0) or (cur.dx < 0 and other.dx >= 0):
-                            continue
-                        if xx[-1] == _x_at(other, y):
-                            off = -1 if y == ymax else 1
-                            a = _x_at(cur, y + off)
-                            b = _x_at(other, y + off)
-                            if y == cur.ymax:
-                                val = F32(max(a, b) + F32(1)) if cur.dx > 0 else F32(min(a, b) - F32(1))
-                            else:
-                                val = F32(min(a, b)) if cur.dx > 0 else F32(max(a, b) + F32(1))
-                            if k < len(xx):
-                                xx[k] = val
-                            break
-        xx.sort()
-        j = len(xx)
-        x_pos = -1 if j == 0 else 0
-        for i in range(1, j, 2):
-            x_end = _round_down(float(xx[i]))
-            if x_end < x_pos:
+            if not (cur.ymin <= y <= cur.ymax):
                 continue
-            x_start = _round_up(float(xx[i - 1]))
-            if x_pos > x_start:
-                x_start = x_pos
-                if x_end < x_start:
-                    continue
-            _hline(img, x_start, y, x_end, ink)
-            x_pos = x_end + 1
-
-
-def _is_int_roundf(v) -> bool:
-    # roundf(x) == x  <=>  x is integral (C roundf rounds half away from zero; equality only for integers)
-    return float(v) == math.floor(float(v))
+            x = _x_at(cur, y)
+            if y == cur.ymax and y < ymax:
+                xx.append(x)
+                xx.append(x)
+                continue
+            if (y == cur.ymin or y == cur.ymax) and cur.dx != 0:
+                adj = y - 1 if y == cur.ymax else y + 1
+                for k in range(i):
+                    other = table[k]
+                    if y != other.ymin and y != other.ymax:
+                        continue
+                    if other.dx == 0:
+                        continue
+                    if _roundf(x) != _roundf(_x_at(other, y)):
+                        continue
+                    if adj < other.ymin or adj > other.ymax:
+                        continue
+                    a, b = _x_at(cur, adj), _x_at(other, adj)
+                    one = F32(1.0)
+                    if x > F32(a + one) and x > F32(b + one):
+                        x = F32(_roundf(max(a, b)) + one)
+                    elif F32(a - one) > x and F32(b - one) > x:
+                        x = F32(_roundf(min(a, b)) - one)
+                    break
+            xx.append(x)
+        xx.sort()
+        for i in range(1, len(xx), 2):
+            _hline(img, _round_up(float(xx[i - 1])), y, _round_down(float(xx[i])), ink)
 
 
 def polygon_mask(polys, width: int, height: int) -> np.ndarray:

@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(_HERE, "libhipac_b200.so")
 # the same library with -DHIPAC_DEBUG_BOUNDS (device-side bounds assertions in the stage-1 kernels); loaded instead of
 # LIB_PATH when HIPAC_DEBUG_BOUNDS=1 is in the environment (tests/test_debug_bounds_gpu.py runs it in a subprocess)
 DBG_LIB_PATH = os.path.join(_HERE, "libhipac_b200_dbg.so")
-SOURCES = ["capi.cu", "tile_scan.cu", "resnet18.cu", "exchange.cu", "debug_umma.cu"]
+SOURCES = ["capi.cu", "tile_scan.cu", "resnet18.cu", "exchange.cu", "polygon.cu", "debug_umma.cu"]
 HEADER = os.path.join(os.path.dirname(_HERE), "include", "hipac_b200.h")
 
 LAYOUT_NHWC3_BF16 = 1
@@ -153,6 +153,12 @@ def _declare(l):
     l.hipac_exchange_pack.argtypes = [vp, vp, vp, vp, i32, i32, vp, i32, i32, vp, vp]
     l.hipac_exchange_merge.restype = i32
     l.hipac_exchange_merge.argtypes = [vp, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, i32, vp, sz, vp]
+    l.hipac_polygon_workspace_bytes.restype = sz
+    l.hipac_polygon_workspace_bytes.argtypes = [i32]
+    l.hipac_polygon_fill.restype = i32
+    l.hipac_polygon_fill.argtypes = [vp, vp, i32, vp, vp, i32, i32, i64, i32, i32, i32, vp, sz, vp]
+    l.hipac_polygon_overflowed.restype = i32
+    l.hipac_polygon_overflowed.argtypes = [vp, vp]
     l.hipac_debug_umma_shift.restype = i32
     l.hipac_debug_umma_shift.argtypes = [vp, vp, vp, i32, i32, vp]
     l.hipac_profile_enable.restype = i32
@@ -168,7 +174,8 @@ EXPORTS = [
     "hipac_tile_scan", "hipac_upload_rows", "hipac_tile_scan_set_count_buffer", "hipac_tile_scan_wait_count", "hipac_pillow_coeffs", "hipac_normalize_lut_bf16", "hipac_resnet18_packed_bytes",
     "hipac_resnet18_pack", "hipac_resnet18_workspace_bytes", "hipac_resnet18_forward", "hipac_resnet18_forward_dcount",
     "hipac_resnet18_conv_layer", "hipac_exchange_row_bytes", "hipac_exchange_segment_bytes", "hipac_exchange_workspace_bytes",
-    "hipac_exchange_pack", "hipac_exchange_merge", "hipac_profile_enable", "hipac_profile_report", "hipac_debug_umma_shift", "hipac_resnet18_stem", "hipac_resnet18_conv_ds_fused",
+    "hipac_exchange_pack", "hipac_exchange_merge", "hipac_polygon_workspace_bytes", "hipac_polygon_fill", "hipac_polygon_overflowed",
+    "hipac_profile_enable", "hipac_profile_report", "hipac_debug_umma_shift", "hipac_resnet18_stem", "hipac_resnet18_conv_ds_fused",
 ]
 
 
