@@ -149,6 +149,36 @@ def bind_near_gpu(index: int):
     return None
 
 
+_period_mask = None
+
+
+def lesion_polygons(world: int = 1):
+    """The slide's lesion ANNOTATIONS: the synthetic lesion ellipses as 720-vertex integer polygons, one copy per 16384-row
+    period of the N x 16384-row slide (what a CAMELYON16 XML holds, after parse_xml_mask's int(x * scale) truncation,
+    reference src/main.py:388-405)."""
+    from ss25_hierarchical_multiscale_image_classification_b200.synthetic import _geometry
+    _, lesion, _, _ = _geometry(SEED, LEVEL, WIDTH, ROWS_PER_GPU)
+    t = np.linspace(0.0, 2.0 * np.pi, 720, endpoint=False)
+    base = [np.stack([(cx + rx * np.cos(t)).astype(np.int64), (cy + ry * np.sin(t)).astype(np.int64)], 1).astype(np.int32)
+            for cx, cy, rx, ry in lesion]
+    return [p + np.array([0, k * ROWS_PER_GPU], np.int32) for k in range(world) for p in base]
+
+
+def period_mask():
+    """uint8 [16384, 16384] lesion mask of one period, rasterised on the HOST the way the reference does it:
+    ImageDraw.polygon(coords, outline=255, fill=255) per annotation (src/main.py:392-409).  Input of the CPU arms and the
+    cross-check of the device rasteriser."""
+    global _period_mask
+    if _period_mask is None:
+        from PIL import Image, ImageDraw
+        im = Image.new("L", (WIDTH, ROWS_PER_GPU), 0)
+        d = ImageDraw.Draw(im)
+        for p in lesion_polygons(1):
+            d.polygon([(int(x), int(y)) for x, y in p], outline=255, fill=255)
+        _period_mask = np.array(im)
+    return _period_mask
+
+
 def shard_rows(ny_total: int, world: int, rank: int):
     """Contiguous candidate tile-row range of `rank` (balanced by row count)."""
     base, rem = divmod(ny_total, world)
@@ -163,8 +193,9 @@ def build_slab(world: int, rank: int, pinned: bool = True):
     work really is fixed as N grows: every rank tiles the same tissue layout; only the last rank sees the slide's
     bottom edge (white-padded patches), exactly like the single rank at N = 1."""
     import torch
-    from ss25_hierarchical_multiscale_image_classification_b200.synthetic import make_lesion_mask, make_level
+    from ss25_hierarchical_multiscale_image_classification_b200.synthetic import make_level
     H = ROWS_PER_GPU * world
+    pm = period_mask()
     ny_total = (H + STRIDE - 1) // STRIDE
     i0, i1 = shard_rows(ny_total, world, rank)
     y0, y1 = i0 * STRIDE, min(H, (i1 - 1) * STRIDE + PATCH)
@@ -180,7 +211,7 @@ def build_slab(world: int, rank: int, pinned: bool = True):
             q = r % ROWS_PER_GPU
             n = min(r1 - r, ROWS_PER_GPU - q)
             inp[r - y0:r - y0 + n] = make_level(SEED, LEVEL, WIDTH, ROWS_PER_GPU, q, q + n)
-            mnp[r - y0:r - y0 + n] = make_lesion_mask(SEED, LEVEL, WIDTH, ROWS_PER_GPU, q, q + n)
+            mnp[r - y0:r - y0 + n] = pm[q:q + n]
             r += n
 
     from concurrent.futures import ThreadPoolExecutor
@@ -216,7 +247,14 @@ def run_ours(args):
     net = seeded_resnet18(seed=0, classifier=True)                        # random-init weights (BASELINE config)
     packed = features.pack_resnet18(net.state_dict(), dev)
     img_h, msk_h, (i0, i1, y0, H) = build_slab(world, rank)
-    img_d, msk_d = img_h.to(dev), msk_h.to(dev)
+    # the lesion mask is born on the GPU: hipac_polygon_fill rasterises the annotation polygons (bit-exact against the
+    # Pillow call of the reference's parse_xml_mask); msk_h -- the same polygons rasterised by Pillow on the host -- is
+    # what the CPU arms read and the cross-check below
+    from ss25_hierarchical_multiscale_image_classification_b200.preprocessing import lesion_mask as lm
+    polys = lm.PolygonSet(lesion_polygons(world), dev)
+    img_d = img_h.to(dev)
+    msk_d = lm.rasterize_polygons(polys, WIDTH, H, dev, y_begin=y0, n_rows=int(img_h.shape[0]))
+    mask_equal = bool(torch.equal(msk_d.cpu(), msk_h))
     rows = (0, i1 - i0)
     n_cand = ((WIDTH + STRIDE - 1) // STRIDE) * (i1 - i0)
     pipe = pipeline.HostPipeline(int(img_h.shape[0]), WIDTH, dev, with_mask=True, num_classes=2)
@@ -248,8 +286,8 @@ def run_ours(args):
     def step_e2e():
         # host buffers in, host buffers out: pinned H2D of image + mask (overlapped with compute by row groups),
         # D2H of coords / labels / features / logits; process_level_host synchronises before returning
-        r = pipeline.process_level_host(img_h, msk_h, LEVEL, packed, pipe, stride=None, row_range=rows,
-                                        groups=args.groups, chunk=args.chunk, exchange=xchg_e2e, y_offset=y0)
+        r = pipeline.process_level_host(img_h, polys, LEVEL, packed, pipe, stride=None, row_range=rows,
+                                        groups=args.groups, chunk=args.chunk, exchange=xchg_e2e, y_offset=y0, polygon_window=(H, y0))
         return len(r), len(r)
 
     def timed(fn, steps, warmup):
@@ -354,14 +392,15 @@ def run_ours(args):
                    "resnet_chunk": args.chunk, "e2e_upload_groups": args.groups, "host_threads_per_rank": host_threads, "cpus_near_gpu": near_cpus},
         "e2e": {"value": round(total_surv_e / (ms_e2e * 1e-3), 1), "unit": "patches/s",
                 "h2d_bytes_per_step": int(pipe.last_h2d_bytes),
-                "h2d_note": "image rows once + the non-zero 32-row blocks of the lesion mask (host block-max scan inside the "
-                            f"timed region); dense input is {int(img_h.numel() + msk_h.numel())} bytes",
+                "h2d_note": "the level image rows, once; the lesion mask never crosses PCIe: the annotation polygons "
+                            f"({int(polys.xy.nbytes)} bytes of vertices, resident) are rasterised on the GPU every step (hipac_polygon_fill)",
                 "d2h_bytes_per_step": int(n_e2e_rows * (512 * 4 + 2 * 4 + 8 + 1) + 8),
                 "d2h_note": "coords + labels + features + logits of every row this rank returns to its host (N > 1: the gathered set)",
                 "ms_per_step": round(ms_e2e, 3)},
         "gpu_launches": launches,
         "clocks": clk.summary(),
         "patch_set_crc32": f"{crc:08x}", "patch_set_in_canonical_order": canonical,
+        "lesion_mask_device_equals_pillow": mask_equal,
         "roofline": {"bound": "tensor", "kernel": f"conv stack: k_conv1_pool + k_conv3x3_rows + k_conv_umma ({sum(v['launches'] for v in conv.values()) // 2} launches = 20 conv layers per step)",
                      "achieved": round(conv_tf, 1),
                      "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
@@ -399,8 +438,9 @@ def cpu_sample_regions(budget_candidates: int):
     """Every-k-th candidate of the N=1 workload with its source pixels pre-generated (so synthetic-data
     generation is NOT timed as reference work; the reference would get them from read_region)."""
     from concurrent.futures import ThreadPoolExecutor
-    from ss25_hierarchical_multiscale_image_classification_b200.synthetic import make_lesion_mask, make_level
+    from ss25_hierarchical_multiscale_image_classification_b200.synthetic import make_level
     H = ROWS_PER_GPU
+    pm = period_mask()
     nx, ny = (WIDTH + STRIDE - 1) // STRIDE, (H + STRIDE - 1) // STRIDE
     k = max(1, (nx * ny) // budget_candidates)
     cands = [(ix * STRIDE, iy * STRIDE) for ix in range(nx) for iy in range(ny)]
@@ -409,8 +449,7 @@ def cpu_sample_regions(budget_candidates: int):
     def gen(xy):
         x, y = xy
         w, h = min(PATCH, WIDTH - x), min(PATCH, H - y)
-        return xy, (make_level(SEED, LEVEL, WIDTH, H, y, y + h, x, x + w),
-                    make_lesion_mask(SEED, LEVEL, WIDTH, H, y, y + h)[:, x:x + w])
+        return xy, (make_level(SEED, LEVEL, WIDTH, H, y, y + h, x, x + w), np.ascontiguousarray(pm[y:y + h, x:x + w]))
 
     with ThreadPoolExecutor(min(16, os.cpu_count() or 8)) as ex:
         cache = dict(ex.map(gen, sample))
@@ -496,7 +535,7 @@ def reference_slide():
     global _ref_slide
     if _ref_slide is None:
         from ss25_hierarchical_multiscale_image_classification_b200.synthetic import SyntheticSlide
-        img, msk, _ = build_slab(1, 0, pinned=False)
+        img, msk, _ = build_slab(1, 0, pinned=False)          # msk = the annotation polygons rasterised by Pillow (period_mask)
         _ref_slide = (SyntheticSlide(levels=[img.numpy()], name="tumor_900"), msk.numpy())
         from oracle import ref_harness as rh
         rh.load_reference_main()                            # importing the reference's module is not a timed step either

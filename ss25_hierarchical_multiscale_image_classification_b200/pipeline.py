@@ -241,8 +241,13 @@ def upload_group_bounds(i0: int, i1: int, groups: int):
 
 def process_level_host(level_img_host: torch.Tensor, mask_host, level: int, packed: _features.PackedResNet18,
                        pipe: HostPipeline, stride=None, row_range=None, groups: int = 4, chunk: int = 8192,
-                       exchange=None, y_offset: int = 0) -> LevelResult:
+                       exchange=None, y_offset: int = 0, polygon_window=None) -> LevelResult:
     """Same as ``process_level`` for HOST inputs; returns HOST tensors (pinned views, valid until the next call).
+
+    ``mask_host`` is the rasterised lesion mask (uint8 ``[H, W]`` host tensor, uploaded sparsely) OR a
+    ``preprocessing.lesion_mask.PolygonSet``: the annotation polygons themselves, in which case the mask is rasterised on
+    the GPU into the staging buffer (``polygon_window = (level_height, y_begin)`` places this slab inside the level the
+    vertices refer to; default: the slab is the whole level) and no mask byte crosses PCIe.
 
     The candidate grid rows are cut into ``groups`` contiguous groups.  All uploads are queued in row order
     on the copy stream; group ``g`` is scanned as soon as the rows it touches (its own + the
@@ -260,10 +265,22 @@ def process_level_host(level_img_host: torch.Tensor, mask_host, level: int, pack
     dev = pipe.device
     main = torch.cuda.current_stream(dev)
     events, done_rows = [], i0 * S
+    polys = mask_host if (mask_host is not None and not torch.is_tensor(mask_host)) else None
+    if polys is not None:
+        from .preprocessing.lesion_mask import rasterize_polygons
+        if pipe.mask is None:
+            raise ValueError("the pipeline was built without a mask buffer")
+        level_h, y_begin = polygon_window if polygon_window is not None else (H, 0)
+        # the previous step's kernels (same stream) are done with the buffer; the fill clears the slab's rows first
+        rasterize_polygons(polys, W, int(level_h), y_begin=int(y_begin), n_rows=H, out=pipe.mask, check=False)
+        pipe._dirty = []
+        mask_host = None
     with torch.cuda.stream(pipe.copy_stream):
         pipe.copy_stream.wait_stream(main)          # previous step's kernels are done with the staging buffers
-        if pipe.mask is not None:
+        if pipe.mask is not None and polys is None:
             pipe.begin_step()
+        elif polys is not None:
+            pipe.last_h2d_bytes = 0
         for g in range(groups):
             need = min(H, (bounds[g + 1] - 1) * S + P + 8) if bounds[g + 1] > bounds[g] else done_rows
             if need > done_rows:
@@ -274,7 +291,7 @@ def process_level_host(level_img_host: torch.Tensor, mask_host, level: int, pack
             ev = torch.cuda.Event()
             ev.record(pipe.copy_stream)
             events.append(ev)
-    mask_dev = pipe.mask if (pipe.mask is not None and mask_host is not None) else None
+    mask_dev = pipe.mask if (pipe.mask is not None and (mask_host is not None or polys is not None)) else None
     if exchange is not None:
         if exchange.spr < groups:
             raise ValueError(f"exchange has {exchange.spr} segments per rank, {groups} row groups need one each")
