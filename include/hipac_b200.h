@@ -203,6 +203,25 @@ int hipac_exchange_merge(const void* d_segments, int num_segments, int capacity,
                          int32_t* d_coords, uint8_t* d_labels, float* d_feats, float* d_logits, int32_t* d_total,
                          int out_capacity, void* d_workspace, size_t workspace_bytes, void* stream);
 
+/* ---------------------------------------------------------------------------------------
+ * ABMIL head over a bag of patch features: MILAttentionPooling + MILClassifier of the reference
+ * (src/models/mil_classifier.py:5-45), fp32:  a = softmax_i(u . tanh(V x_i + bV) + bu);  M = sum_i a_i x_i;
+ * logits = W2 relu(W1 M + b1) + b2.  pooling: 0 attention, 1 mean (x.mean(0)), 2 max (x.max(0)).
+ *   hipac_mil_pack     host repack of the module's tensors (torch layouts: V [128][512], bV [128], u = attn_U.weight [1][128],
+ *                      bu [1], W1 [128][512], b1 [128], W2 [k][128], b2 [k]; V/bV/u/bu may be NULL for mean / max pooling)
+ *                      into hipac_mil_packed_floats(k) floats; the caller uploads the blob.
+ *   hipac_mil_forward  d_x float32 [n_instances][512] (e.g. hipac_resnet18_forward's features); d_count: optional int32 device
+ *                      counter (min(*d_count, n_instances) instances are pooled, nothing waits on the host);
+ *                      d_logits [k]; d_attention [n_instances] or NULL (attention weights, the module's second output);
+ *                      d_pooled [512] or NULL.
+ * ------------------------------------------------------------------------------------- */
+size_t hipac_mil_packed_floats(int num_classes);
+int hipac_mil_pack(const float* V, const float* bV, const float* u, const float* bu, const float* W1, const float* b1,
+                   const float* W2, const float* b2, int num_classes, float* h_packed);
+size_t hipac_mil_workspace_bytes(int n_instances);
+int hipac_mil_forward(const float* d_x, int n_instances, const int32_t* d_count, const float* d_packed, int num_classes, int pooling,
+                      float* d_logits, float* d_attention, float* d_pooled, void* d_workspace, size_t workspace_bytes, void* stream);
+
 /* Number of kernel launches issued by this library on the calling thread since the last reset
  * (bench.py's "gpu_launches"). */
 long long hipac_launch_count(int reset);

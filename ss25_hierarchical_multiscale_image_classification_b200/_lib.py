@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(_HERE, "libhipac_b200.so")
 # the same library with -DHIPAC_DEBUG_BOUNDS (device-side bounds assertions in the stage-1 kernels); loaded instead of
 # LIB_PATH when HIPAC_DEBUG_BOUNDS=1 is in the environment (tests/test_debug_bounds_gpu.py runs it in a subprocess)
 DBG_LIB_PATH = os.path.join(_HERE, "libhipac_b200_dbg.so")
-SOURCES = ["capi.cu", "tile_scan.cu", "resnet18.cu", "exchange.cu", "polygon.cu", "debug_umma.cu"]
+SOURCES = ["capi.cu", "tile_scan.cu", "resnet18.cu", "exchange.cu", "polygon.cu", "mil.cu", "debug_umma.cu"]
 HEADER = os.path.join(os.path.dirname(_HERE), "include", "hipac_b200.h")
 
 LAYOUT_NHWC3_BF16 = 1
@@ -159,6 +159,14 @@ def _declare(l):
     l.hipac_polygon_fill.argtypes = [vp, vp, i32, vp, vp, i32, i32, i64, i32, i32, i32, vp, sz, vp]
     l.hipac_polygon_overflowed.restype = i32
     l.hipac_polygon_overflowed.argtypes = [vp, vp]
+    l.hipac_mil_packed_floats.restype = sz
+    l.hipac_mil_packed_floats.argtypes = [i32]
+    l.hipac_mil_pack.restype = i32
+    l.hipac_mil_pack.argtypes = [vp] * 8 + [i32, vp]
+    l.hipac_mil_workspace_bytes.restype = sz
+    l.hipac_mil_workspace_bytes.argtypes = [i32]
+    l.hipac_mil_forward.restype = i32
+    l.hipac_mil_forward.argtypes = [vp, i32, vp, vp, i32, i32, vp, vp, vp, vp, sz, vp]
     l.hipac_debug_umma_shift.restype = i32
     l.hipac_debug_umma_shift.argtypes = [vp, vp, vp, i32, i32, vp]
     l.hipac_profile_enable.restype = i32
@@ -174,7 +182,7 @@ EXPORTS = [
     "hipac_tile_scan", "hipac_upload_rows", "hipac_tile_scan_set_count_buffer", "hipac_tile_scan_wait_count", "hipac_pillow_coeffs", "hipac_normalize_lut_bf16", "hipac_resnet18_packed_bytes",
     "hipac_resnet18_pack", "hipac_resnet18_workspace_bytes", "hipac_resnet18_forward", "hipac_resnet18_forward_dcount",
     "hipac_resnet18_conv_layer", "hipac_exchange_row_bytes", "hipac_exchange_segment_bytes", "hipac_exchange_workspace_bytes",
-    "hipac_exchange_pack", "hipac_exchange_merge", "hipac_polygon_workspace_bytes", "hipac_polygon_fill", "hipac_polygon_overflowed",
+    "hipac_exchange_pack", "hipac_exchange_merge", "hipac_polygon_workspace_bytes", "hipac_polygon_fill", "hipac_polygon_overflowed", "hipac_mil_packed_floats", "hipac_mil_pack", "hipac_mil_workspace_bytes", "hipac_mil_forward",
     "hipac_profile_enable", "hipac_profile_report", "hipac_debug_umma_shift", "hipac_resnet18_stem", "hipac_resnet18_conv_ds_fused",
 ]
 
@@ -189,6 +197,9 @@ def lib():
                 raise RuntimeError(
                     f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
                     "(the HiPAC B200 path has no CPU/PyTorch fallback)")
+            if _stale(path):
+                raise RuntimeError(f"{path} was built from different sources than csrc/ now holds: run "
+                                   "`python -c 'import __graft_entry__ as g; g.build()'`")
             l = C.CDLL(path)
             _declare(l)
             _lib = l

@@ -88,9 +88,13 @@ def read_level_rows(slide, level: int, y0: int, y1: int) -> np.ndarray:
     return np.array(region)   # own, writable copy (torch.from_numpy needs one)
 
 
-def scan_slide(slide, level: int, mask: np.ndarray | None, stride=None, patch_size: int = 224, device="cuda",
+def scan_slide(slide, level: int, mask, stride=None, patch_size: int = 224, device="cuda",
                max_slab_bytes: int = 2 << 30, want_u8: bool = False, layout=None, on_slab=None):
     """Run the GPU tile scan over a whole slide level in row slabs that fit ``max_slab_bytes``.
+
+    ``mask``: the rasterised lesion mask (uint8 ``[H, W]`` numpy array, uploaded slab by slab), a
+    ``lesion_mask.PolygonSet`` (the annotation polygons: every slab's mask rows are rasterised on the GPU, Pillow-exact,
+    nothing is uploaded), or ``None`` (every patch "normal").
 
     Returns ``(coords int32 [N,2], labels uint8 [N])`` as numpy arrays in the reference's emission order,
     plus whatever ``on_slab(pb, slab_rgb, y0)`` collected (it is called once per slab with the
@@ -109,7 +113,10 @@ def scan_slide(slide, level: int, mask: np.ndarray | None, stride=None, patch_si
         img = alloc_level_image(y1 - y0, width, device)
         upload_level_rows(img, np.ascontiguousarray(rgb))
         m = None
-        if mask is not None:
+        if mask is not None and not isinstance(mask, np.ndarray):
+            from .lesion_mask import rasterize_polygons
+            m = rasterize_polygons(mask, width, height, device, y_begin=y0, n_rows=y1 - y0)
+        elif mask is not None:
             m = alloc_level_image(y1 - y0, width, device, channels=1)
             upload_level_rows(m, np.ascontiguousarray(mask[y0:y1]))
         # a slab that ends above the image bottom has complete data for its grid rows, so tiling it as its own
@@ -180,8 +187,11 @@ def _extract_one(file, wsi_dir, level_dir, annot_dir_train, annot_dir_test, leve
     mask = None
     if os.path.exists(xml_path):
         try:
-            m = parse_xml_mask(xml_path, (width, height), slide)
-            mask = np.asarray(m) if m is not None else None
+            # same XML walk and vertex arithmetic as parse_xml_mask; the polygons are rasterised on the GPU per slab
+            # (bit-exact against the Pillow call the reference makes), so no level-sized host mask is ever built
+            from .lesion_mask import PolygonSet, annotation_polygons
+            polys = annotation_polygons(xml_path, (width, height), slide)
+            mask = PolygonSet(polys, device) if polys is not None else None
         except Exception as e:
             print(f"{bcolors.WARNING}[WARNING]{bcolors.ENDC} Failed to parse XML for {file}: {e}")
     else:

@@ -117,3 +117,22 @@ def test_heatmap_and_froc_csv(tmp_path):
     rows = [l.split(",") for l in open(tmp_path / "t.csv").read().split()]
     assert n == 2 and rows[0][1:] == [str((448 + 224) * 4), str((224 + 224) * 4)]   # level-0 coordinates of the centre
     assert abs(float(rows[0][0]) - float(p[1])) < 1e-5
+
+
+def test_mil_classifier_cpu_contract():
+    """MILClassifier keeps the reference's constructor, state-dict keys and (logits, attention) return on the CPU path."""
+    import torch
+    from ss25_hierarchical_multiscale_image_classification_b200.models import MILAttentionPooling, MILClassifier
+    torch.manual_seed(0)
+    bag = torch.randn(17, 512)
+    m = MILClassifier(512, num_classes=2, pooling="attention")
+    logits, attn = m(bag)
+    assert logits.shape == (2,) and attn.shape == (17, 1) and abs(float(attn.sum()) - 1) < 1e-5
+    pooled, a = MILAttentionPooling(512)(bag)
+    assert pooled.shape == (512,) and a.shape == (17, 1)
+    for pooling in ("mean", "max"):
+        lg, at = MILClassifier(512, pooling=pooling)(bag)
+        assert lg.shape == (2,) and at is None
+    import pytest
+    with pytest.raises(ValueError):
+        MILClassifier(512, pooling="median")
