@@ -191,6 +191,9 @@ int hipac_resnet18_stem(const void* d_packed, int num_classes, const void* d_in,
  * ------------------------------------------------------------------------------------- */
 #define HIPAC_FEATURE_DIM 512
 /* feat_dim is 512 (rows carry the features) or 0 (coords / labels / logits only, e.g. the heatmap of configs[3]).
+ * cyclic_world: 0 = the segments are stored in ascending y order (contiguous row shards); W > 0 = block-cyclic sharding over W
+ * ranks (stored rank-major, as an all-gather delivers them): local segment g of rank r is grid-row block g * W + r, which balances
+ * spatially clumped tissue across the ranks.
  * hipac_exchange_pack: `capacity` = rows available in the INPUT tensors (<= the segment's row capacity); min(*d_count,
  * capacity) rows are packed.  hipac_exchange_merge: `capacity` = row capacity of every segment (segment stride =
  * hipac_exchange_segment_bytes(capacity, ...)). */
@@ -200,7 +203,7 @@ size_t hipac_exchange_workspace_bytes(int num_segments, int nx);
 int hipac_exchange_pack(const int32_t* d_coords, const uint8_t* d_labels, const float* d_feats, const float* d_logits,
                         int feat_dim, int num_classes, const int32_t* d_count, int capacity, int y_offset, void* d_segment, void* stream);
 int hipac_exchange_merge(const void* d_segments, int num_segments, int capacity, int feat_dim, int num_classes, int stride, int nx,
-                         int32_t* d_coords, uint8_t* d_labels, float* d_feats, float* d_logits, int32_t* d_total,
+                         int cyclic_world, int32_t* d_coords, uint8_t* d_labels, float* d_feats, float* d_logits, int32_t* d_total,
                          int out_capacity, void* d_workspace, size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------

@@ -152,7 +152,7 @@ def _declare(l):
     l.hipac_exchange_pack.restype = i32
     l.hipac_exchange_pack.argtypes = [vp, vp, vp, vp, i32, i32, vp, i32, i32, vp, vp]
     l.hipac_exchange_merge.restype = i32
-    l.hipac_exchange_merge.argtypes = [vp, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, i32, vp, sz, vp]
+    l.hipac_exchange_merge.argtypes = [vp, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, i32, vp, sz, vp]
     l.hipac_polygon_workspace_bytes.restype = sz
     l.hipac_polygon_workspace_bytes.argtypes = [i32]
     l.hipac_polygon_fill.restype = i32

@@ -6,6 +6,7 @@
 #include <stdio.h>
 #include <string.h>
 #include <string>
+#include <utility>
 
 #include "../../include/hipac_b200.h"
 
@@ -51,6 +52,29 @@ int ensure_dyn_smem_impl(const void* func, int bytes);
 template <typename F>
 static inline int ensure_dyn_smem(F* func, int bytes) { return ensure_dyn_smem_impl(reinterpret_cast<const void*>(func), bytes); }
 int device_sm_count(int* sms);
+bool pdl_enabled();   // HIPAC_PDL=0 switches programmatic dependent launch off (A/B and debugging)
+
+// Launch with optional thread-block cluster and programmatic stream serialization (see ptx::pdl_wait in umma.cuh).
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_ex(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, int cluster_x,
+                                    bool pdl, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid, cfg.blockDim = block, cfg.dynamicSmemBytes = smem, cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (cluster_x > 1) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = (unsigned)cluster_x, attr[na].val.clusterDim.y = 1, attr[na].val.clusterDim.z = 1;
+    na++;
+  }
+  if (pdl && pdl_enabled()) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    na++;
+  }
+  cfg.attrs = attr, cfg.numAttrs = (unsigned)na;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
 
 // Device-side bounds assertions of the stage-1 kernels (compute-sanitizer is not available on the B200 pool): compiled
 // in only with -DHIPAC_DEBUG_BOUNDS (libhipac_b200_dbg.so, exercised by tests/test_debug_bounds_gpu.py).

@@ -19,7 +19,10 @@
 //   warps 2.. epilogue: wait the LOCAL tfull, drain their CTA's 128 accumulator rows, arrive on the LEADER's tempty
 #pragma once
 
-template <int BN, int KC, int W, int R, int KDS>
+// TEPI: the epilogue moves through shared-memory staging and TMA (always for BN = 64; for BN = 128 only the RESIDUAL variant,
+// whose per-thread 256-byte residual fetch is what the LSU cannot keep up with -- it trades one region stage for a
+// single staging tile of two 64-channel halves)
+template <int BN, int KC, int W, int R, int KDS, bool TEPI = (BN == 64)>
 struct Row2Cfg {
   static constexpr int Wp = W + 2;
   static constexpr int kRegionRows = 128 + 2 * Wp + 2;
@@ -31,10 +34,11 @@ struct Row2Cfg {
   static constexpr int kNumB = 9 * KC + KDS;
   static constexpr int kBBytes = kNumB * kBBlock;
   // 64-channel tiles leave through shared-memory staging + TMA (see conv_rows_tma.cuh): [warpgroup][buffer] tiles of R x W x 128 B
-  static constexpr bool kTmaEpi = BN == 64;
-  static constexpr int kTileBytes = R * W * 128;
+  static constexpr bool kTmaEpi = TEPI;
+  static constexpr int kTileBytes = R * W * 128;                                  // one 64-channel half of an output tile
   static constexpr int kStageBytes = (kTileBytes + 1023) / 1024 * 1024;
-  static constexpr int kStagingBytes = kTmaEpi ? 4 * kStageBytes : 0;
+  // BN = 64: [warpgroup][buffer] = 4 tiles; BN = 128: ONE tile of two 64-channel halves
+  static constexpr int kStagingBytes = !kTmaEpi ? 0 : (BN == 64 ? 4 : 2) * kStageBytes;
   static constexpr int kFree = 232448 - 1024 - 512 - kBBytes - kStagingBytes;
   static constexpr int kAStages = kFree / kRegionBytes >= 4 ? 4 : kFree / kRegionBytes;
   static constexpr int kTmemCols = 2 * BN;
@@ -44,12 +48,12 @@ struct Row2Cfg {
   static_assert(kSmemBytes <= 232448, "shared memory budget");
 };
 
-template <int BN, int KC, int W, int R, int KDS>
+template <int BN, int KC, int W, int R, int KDS, bool TEPI = (BN == 64)>
 __global__ void __launch_bounds__(conv_threads(BN), 1)
 k_conv3x3_rows2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmO,
                 const __grid_constant__ CUtensorMap tmR, const RowConvParams p) {
-  using Cfg = Row2Cfg<BN, KC, W, R, KDS>;
+  using Cfg = Row2Cfg<BN, KC, W, R, KDS, TEPI>;
   constexpr int Wp = Cfg::Wp, H = W, TILES_PER_IMG = H / R, NS = Cfg::kAStages, SLICES = KC + KDS;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -67,6 +71,7 @@ k_conv3x3_rows2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = ptx::cluster_ctarank();
   const bool leader = rank == 0;
+  ptx::pdl_launch_dependents();
   if (threadIdx.x == 0) {
     ptx::prefetch_tensormap(&tmA);
     ptx::prefetch_tensormap(&tmB);
@@ -89,6 +94,15 @@ k_conv3x3_rows2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   ptx::cluster_sync_all();          // barriers of both CTAs initialised before any remote arrive / multicast commit
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (warp == 0) {   // this CTA's half of the resident weights: constant data, loaded before the dependency wait
+    if (ptx::elect_one()) {
+      if (leader) ptx::mbar_arrive_expect_tx(b_full, 2 * Cfg::kBBytes);
+      else ptx::mbar_arrive_cluster(b_full, 0);
+      for (int kb = 0; kb < Cfg::kNumB; kb++) ptx::tma2_load_2d(sB + kb * Cfg::kBBlock, &tmB, b_full, kb * 64, (int)rank * Cfg::kBHalf);
+    }
+    __syncwarp();
+  }
+  ptx::pdl_wait();
   const int num_tiles = effective_patches(p.n_dev, p.n_base, p.n_img) * (p.num_tiles / p.n_img);
   const int num_pairs = (num_tiles + 1) >> 1;
   const int pair0 = blockIdx.x >> 1, pair_step = gridDim.x >> 1;
@@ -102,12 +116,6 @@ k_conv3x3_rows2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 
   if (warp == 0) {
     // ===================== TMA producer (both CTAs) =====================
-    if (ptx::elect_one()) {
-      if (leader) ptx::mbar_arrive_expect_tx(b_full, 2 * Cfg::kBBytes);
-      else ptx::mbar_arrive_cluster(b_full, 0);
-      for (int kb = 0; kb < Cfg::kNumB; kb++) ptx::tma2_load_2d(sB + kb * Cfg::kBBlock, &tmB, b_full, kb * 64, (int)rank * Cfg::kBHalf);
-    }
-    __syncwarp();
     int sa = 0;
     uint32_t pa = 0;
     for (int tp = pair0; tp < num_pairs; tp += pair_step) {
@@ -170,6 +178,81 @@ k_conv3x3_rows2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         if (acc == 0) acc_phase ^= 1;
       }
     }
+  } else if constexpr (Cfg::kTmaEpi && BN == 128) {
+    // ===================== epilogue, 128 channels with residual: one staging tile of two 64-channel halves =====================
+    // thread 0 owns the bulk groups: store of tile j -> wait until it has been read -> residual load of tile j + 1 into the
+    // same buffer (the MMAs of tile j + 1 run meanwhile: the accumulators are double buffered in TMEM)
+    const int wq = warp & 3;
+    const int gt = threadIdx.x - 64;
+    const int pos = wq * 32 + lane;
+    const int rr = pos / Wp, x = pos - rr * Wp;
+    const bool in_tile = rr < R && x < W;
+    const int srow = rr * W + x;
+    const bool has_res = p.residual != nullptr;
+    uint64_t* ready = st_ready;
+    auto prepare = [&](int tp) {
+      bool active;
+      const int vt = tile_of(tp, active);
+      if (has_res && active) {
+        const int img = vt / TILES_PER_IMG, p0 = (vt - img * TILES_PER_IMG) * R;
+        ptx::mbar_arrive_expect_tx(&ready[0], 2 * Cfg::kTileBytes);
+        ptx::tma_load_4d(sO, &tmR, &ready[0], 0, 0, p0, img);
+        ptx::tma_load_4d(sO + Cfg::kStageBytes, &tmR, &ready[0], 64, 0, p0, img);
+      } else {
+        ptx::mbar_arrive(&ready[0]);
+      }
+    };
+    if (gt == 0 && pair0 < num_pairs) prepare(pair0);
+    int it = 0;
+    for (int tp = pair0; tp < num_pairs; tp += pair_step, ++it) {
+      const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
+      bool active;
+      const int vt = tile_of(tp, active);
+      ptx::mbar_wait(&ready[0], it & 1);
+      ptx::mbar_wait(&tfull[acc], acc_phase);
+      ptx::tc_fence_after();
+      const uint32_t trow = tmem_base + ((uint32_t)(wq * 32) << 16) + acc * BN;
+#pragma unroll
+      for (int half = 0; half < 2; half++) {
+        uint32_t v0[32], v1[32];
+        ptx::tmem_ld_32x32b_x32(trow + half * 64, v0);
+        ptx::tmem_ld_32x32b_x32(trow + half * 64 + 32, v1);
+        ptx::tmem_ld_wait();
+        if (half == 1) {
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if (leader) ptx::mbar_arrive(&tempty[acc]);
+            else ptx::mbar_arrive_cluster(&tempty[acc], 0);
+          }
+        }
+        if (in_tile && active) {
+          uint4* row = reinterpret_cast<uint4*>(sO + half * Cfg::kStageBytes + srow * 128);
+#pragma unroll
+          for (int i = 0; i < 8; i++) {
+            const int ph = i ^ (srow & 7);
+            uint4 res = make_uint4(0u, 0u, 0u, 0u);
+            if (has_res) res = row[ph];
+            row[ph] = epilogue_chunk8(i < 4 ? &v0[8 * i] : &v1[8 * (i - 4)], p.bias + half * 64 + 8 * i, res, has_res, p.relu);
+          }
+        }
+      }
+      ptx::fence_proxy_async();
+      ptx::named_bar_sync(1, 128);
+      if (gt == 0) {
+        if (active) {
+          const int img = vt / TILES_PER_IMG, p0 = (vt - img * TILES_PER_IMG) * R;
+          ptx::tma_store_4d(&tmO, sO, 0, 0, p0, img);
+          ptx::tma_store_4d(&tmO, sO + Cfg::kStageBytes, 64, 0, p0, img);
+        }
+        ptx::bulk_commit_group();
+        if (tp + pair_step < num_pairs) {
+          ptx::bulk_wait_group_read<0>();
+          prepare(tp + pair_step);
+        }
+      }
+    }
+    if (gt == 0) ptx::bulk_wait_group<0>();
   } else if constexpr (Cfg::kTmaEpi) {
     // ===================== epilogue, 64 channels: TMEM -> staging tile (residual in place) -> TMA store =====================
     // (same protocol as k_conv3x3_rows_tma; the accumulator-drained arrive goes to the LEADER's tempty barrier)

@@ -70,6 +70,7 @@ k_conv3x3_rows_tma(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(st_ready + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  ptx::pdl_launch_dependents();
   if (threadIdx.x == 0) {
     ptx::prefetch_tensormap(&tmA);
     ptx::prefetch_tensormap(&tmB);
@@ -89,15 +90,18 @@ k_conv3x3_rows_tma(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const int num_tiles = effective_patches(p.n_dev, p.n_base, p.n_img) * (p.num_tiles / p.n_img);
-
-  if (warp == 0) {
-    // ===================== TMA producer =====================
+  if (warp == 0) {   // resident weights: constant data, loaded before the dependency wait
     if (ptx::elect_one()) {
       ptx::mbar_arrive_expect_tx(b_full, Cfg::kBBytes);
       for (int kb = 0; kb < 9 * KC; kb++) ptx::tma_load_2d(sB + kb * Cfg::kBBlock, &tmB, b_full, kb * 64, 0);
     }
     __syncwarp();
+  }
+  ptx::pdl_wait();
+  const int num_tiles = effective_patches(p.n_dev, p.n_base, p.n_img) * (p.num_tiles / p.n_img);
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
     int sa = 0;
     uint32_t pa = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {

@@ -59,6 +59,7 @@ k_conv1_pool(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  ptx::pdl_launch_dependents();
   if (threadIdx.x == 0) {
     ptx::prefetch_tensormap(&tmA);
     ptx::prefetch_tensormap(&tmB);
@@ -76,15 +77,18 @@ k_conv1_pool(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   constexpr int BLOCKS_PER_IMG = 56 / kStemPB;
-  const int num_blocks = effective_patches(p.n_dev, p.n_base, p.num_blocks / BLOCKS_PER_IMG) * BLOCKS_PER_IMG;
-
-  if (warp == 0) {
-    // ===================== TMA producer =====================
+  if (warp == 0) {   // resident weights: constant data, loaded before the dependency wait
     if (ptx::elect_one()) {
       ptx::mbar_arrive_expect_tx(w_full, kStemWBytes);
       for (int kb = 0; kb < 4; kb++) ptx::tma_load_2d(sW + kb * 8192, &tmB, w_full, kb * 64, 0);
     }
     __syncwarp();
+  }
+  ptx::pdl_wait();
+  const int num_blocks = effective_patches(p.n_dev, p.n_base, p.num_blocks / BLOCKS_PER_IMG) * BLOCKS_PER_IMG;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
     int s = 0;
     uint32_t ph = 0;
     for (int blk = blockIdx.x; blk < num_blocks; blk += gridDim.x) {

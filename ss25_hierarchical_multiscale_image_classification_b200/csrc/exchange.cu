@@ -54,11 +54,20 @@ __global__ void __launch_bounds__(256) k_exchange_pack(const int32_t* __restrict
   }
 }
 
-// Single CTA.  colstart[s][ix] = first row of segment s whose x >= ix * stride (ix = nx: the segment's count);
-// base[ix * nseg + s] = final position of the first row of (column ix, segment s).
+// Single CTA.  colstart[s][ix] = first row of stored segment s whose x >= ix * stride (ix = nx: the segment's count);
+// base[ix * nseg + order(s)] = final position of the first row of (column ix, segment s).
+// y-order rank of stored segment s.  Natural layout (cyc_world = 0): segments are stored in ascending y order.  Block-cyclic
+// sharding (cyc_world = W ranks, spr segments each, stored rank-major as an all-gather delivers them): local segment g of
+// rank r is grid-row block g * W + r of the level.
+__device__ __forceinline__ int seg_order(int s, int nseg, int cyc_world) {
+  if (cyc_world <= 0) return s;
+  const int spr = nseg / cyc_world;
+  return (s % spr) * cyc_world + s / spr;
+}
+
 __global__ void __launch_bounds__(1024) k_exchange_index(const uint8_t* __restrict__ recv, int nseg, int seg_rows, int row_bytes,
-                                                         int stride, int nx, int32_t* __restrict__ colstart, int32_t* __restrict__ base,
-                                                         int32_t* __restrict__ total, int out_capacity) {
+                                                         int stride, int nx, int cyc_world, int32_t* __restrict__ colstart,
+                                                         int32_t* __restrict__ base, int32_t* __restrict__ total, int out_capacity) {
   const size_t seg_bytes = (size_t)(1 + seg_rows) * row_bytes;
   for (int t = threadIdx.x; t < nseg * (nx + 1); t += blockDim.x) {
     const int s = t / (nx + 1), ix = t - s * (nx + 1);
@@ -88,8 +97,13 @@ __global__ void __launch_bounds__(1024) k_exchange_index(const uint8_t* __restri
   for (int k0 = 0; k0 < n; k0 += 1024) {
     const int k = k0 + threadIdx.x;
     int len = 0;
-    if (k < n) {
-      const int ix = k / nseg, s = k - ix * nseg;
+    if (k < n) {   // k = ix * nseg + (y-order rank); the segment holding that rank is found by inverting seg_order
+      const int ix = k / nseg, o = k - ix * nseg;
+      int s = o;
+      if (cyc_world > 0) {
+        const int spr = nseg / cyc_world;
+        s = (o % cyc_world) * spr + o / cyc_world;
+      }
       len = colstart[s * (nx + 1) + ix + 1] - colstart[s * (nx + 1) + ix];
     }
     int inc = len;
@@ -118,7 +132,7 @@ __global__ void __launch_bounds__(1024) k_exchange_index(const uint8_t* __restri
 
 // one warp per gathered row
 __global__ void __launch_bounds__(256) k_exchange_scatter(const uint8_t* __restrict__ recv, int nseg, int seg_rows, int row_bytes,
-                                                          int stride, int nx, const int32_t* __restrict__ colstart,
+                                                          int stride, int nx, int cyc_world, const int32_t* __restrict__ colstart,
                                                           const int32_t* __restrict__ base, int feat_dim, int num_classes,
                                                           int32_t* __restrict__ coords,
                                                           uint8_t* __restrict__ labels, float* __restrict__ feats,
@@ -133,7 +147,7 @@ __global__ void __launch_bounds__(256) k_exchange_scatter(const uint8_t* __restr
   const uint8_t* row = seg + (size_t)(1 + i) * row_bytes;
   const int4 h = *reinterpret_cast<const int4*>(row);
   const int ix = min(h.x / stride, nx - 1);
-  const int dst = base[ix * nseg + s] + (i - colstart[s * (nx + 1) + ix]);
+  const int dst = base[ix * nseg + seg_order(s, nseg, cyc_world)] + (i - colstart[s * (nx + 1) + ix]);
   if (dst < 0 || dst >= out_capacity) return;
   if (lane == 0) {
     coords[2 * dst] = h.x, coords[2 * dst + 1] = h.y;
@@ -192,11 +206,12 @@ extern "C" int hipac_exchange_pack(const int32_t* d_coords, const uint8_t* d_lab
 }
 
 extern "C" int hipac_exchange_merge(const void* d_segments, int num_segments, int capacity, int feat_dim, int num_classes, int stride, int nx,
-                                    int32_t* d_coords, uint8_t* d_labels, float* d_feats, float* d_logits, int32_t* d_total,
+                                    int cyclic_world, int32_t* d_coords, uint8_t* d_labels, float* d_feats, float* d_logits, int32_t* d_total,
                                     int out_capacity, void* d_workspace, size_t workspace_bytes, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   HIPAC_REQUIRE(d_segments && d_coords && d_labels && d_total && d_workspace, "null pointer");
   HIPAC_REQUIRE(num_segments > 0 && capacity >= 0 && stride > 0 && nx > 0 && out_capacity >= 0, "bad geometry");
+  HIPAC_REQUIRE(cyclic_world >= 0 && (cyclic_world == 0 || num_segments % cyclic_world == 0), "cyclic_world must divide num_segments");
   HIPAC_REQUIRE(xchg_dims_ok(feat_dim, num_classes), "feat_dim must be 0 or 512, num_classes in [0, 1024]");
   HIPAC_REQUIRE((num_classes == 0 || d_logits) && (feat_dim == 0 || d_feats), "feature / logit buffer missing");
   HIPAC_REQUIRE(workspace_bytes >= hipac_exchange_workspace_bytes(num_segments, nx), "workspace too small");
@@ -208,13 +223,13 @@ extern "C" int hipac_exchange_merge(const void* d_segments, int num_segments, in
   const uint8_t* recv = reinterpret_cast<const uint8_t*>(d_segments);
   {
     ProfileScope ps("exchange_index", stream, 0.0);
-    k_exchange_index<<<1, 1024, 0, stream>>>(recv, num_segments, capacity, row_bytes, stride, nx, colstart, base, d_total, out_capacity);
+    k_exchange_index<<<1, 1024, 0, stream>>>(recv, num_segments, capacity, row_bytes, stride, nx, cyclic_world, colstart, base, d_total, out_capacity);
   }
   count_launch(1);
   const int64_t warps = (int64_t)num_segments * capacity;
   if (warps > 0) {
     ProfileScope ps("exchange_scatter", stream, (double)warps * row_bytes);
-    k_exchange_scatter<<<(unsigned)((warps + 7) / 8), 256, 0, stream>>>(recv, num_segments, capacity, row_bytes, stride, nx, colstart, base,
+    k_exchange_scatter<<<(unsigned)((warps + 7) / 8), 256, 0, stream>>>(recv, num_segments, capacity, row_bytes, stride, nx, cyclic_world, colstart, base,
                                                                       feat_dim, num_classes, d_coords, d_labels, d_feats,
                                                                       num_classes ? d_logits : nullptr, out_capacity);
     count_launch(1);

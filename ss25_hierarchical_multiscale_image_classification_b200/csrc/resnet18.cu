@@ -128,35 +128,44 @@ __device__ __forceinline__ void epilogue_row(uint32_t tmem_row, const float* __r
   }
 }
 
-template <int BN>
+// RESB: the whole weight matrix (<= kResBlocks k-blocks of [BN x 64]) stays resident in shared memory for the lifetime of the
+// persistent CTA and the ring carries the im2col A tiles only.  Used where it fits (layer2.0.conv1: 9 x 16 KB): the
+// streamed form re-reads 16 KB of weights from L2 per 16 KB of activations, which makes that layer L2-bandwidth bound.
+template <int BN, bool RESB = false>
 struct ConvCfg {
   static constexpr int kBBytes = BN * 128;
-  static constexpr int kStage = kABytes + kBBytes;
-  static constexpr int kStages = BN == 256 ? 4 : 6;
+  static constexpr int kResBlocks = RESB ? 9 : 0;
+  static constexpr int kStage = RESB ? kABytes : kABytes + kBBytes;
+  static constexpr int kStages = RESB ? 4 : (BN == 256 ? 4 : 6);
   static constexpr int kTmemCols = 2 * BN;
-  static constexpr int kSmemBytes = kStages * kStage + 1024 /*alignment slack*/ + 256 /*barriers*/;
+  static constexpr int kSmemBytes = kStages * kStage + kResBlocks * kBBytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
+  static_assert(kSmemBytes <= 232448, "shared memory budget");
 };
 
-template <int BN>
+template <int BN, bool RESB = false>
 __global__ void __launch_bounds__(conv_threads(BN), 1)
 k_conv_umma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const __grid_constant__ CUtensorMap tmA2, const ConvParams p) {
-  using Cfg = ConvCfg<BN>;
+  using Cfg = ConvCfg<BN, RESB>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full = reinterpret_cast<uint64_t*>(base + Cfg::kStages * Cfg::kStage);
+  uint8_t* resB = base + Cfg::kStages * Cfg::kStage;
+  uint64_t* full = reinterpret_cast<uint64_t*>(resB + Cfg::kResBlocks * Cfg::kBBytes);
   uint64_t* empty = full + Cfg::kStages;
   uint64_t* tfull = empty + Cfg::kStages;
   uint64_t* tempty = tfull + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint64_t* b_full = tempty + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_full + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  ptx::pdl_launch_dependents();
   if (threadIdx.x == 0) {
     ptx::prefetch_tensormap(&tmA);
     ptx::prefetch_tensormap(&tmB);
     if (p.num_kb2) ptx::prefetch_tensormap(&tmA2);
     for (int s = 0; s < Cfg::kStages; s++) ptx::mbar_init(&full[s], 1), ptx::mbar_init(&empty[s], 1);
     for (int a = 0; a < 2; a++) ptx::mbar_init(&tfull[a], 1), ptx::mbar_init(&tempty[a], 4);
+    ptx::mbar_init(b_full, 1);
     ptx::fence_barrier_init();
   }
   if (warp == 1) {
@@ -167,6 +176,14 @@ k_conv_umma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (RESB && warp == 0) {   // resident weights: constant data, loaded before the dependency wait
+    if (ptx::elect_one()) {
+      ptx::mbar_arrive_expect_tx(b_full, (uint32_t)(p.num_kb * Cfg::kBBytes));
+      for (int kb = 0; kb < p.num_kb; kb++) ptx::tma_load_2d(resB + kb * Cfg::kBBytes, &tmB, b_full, kb * 64, 0);
+    }
+    __syncwarp();
+  }
+  ptx::pdl_wait();           // the producer kernel's activations (and the device-side patch count) are visible from here on
   const int M_total = effective_patches(p.n_dev, p.n_base, p.M_total / p.hw_out) * p.hw_out;
   const int num_tiles = ((M_total + kBM - 1) / kBM) * p.num_n_tiles;
 
@@ -196,7 +213,7 @@ k_conv_umma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               ptx::tma_load_im2col_4d(a_dst, &tmA, &full[stage], kc * 64, cw, ch, img, (uint16_t)s, (uint16_t)r);
             else  // fused projection shortcut: 1x1 / stride2 / pad 0 over the block input, channels (kb - num_kb) * 64
               ptx::tma_load_im2col_4d(a_dst, &tmA2, &full[stage], (kb - p.num_kb) * 64, q0 * p.stride2, p0 * p.stride2, img, 0, 0);
-            ptx::tma_load_2d(b_dst, &tmB, &full[stage], kb * 64, n_tile * BN);
+            if (!RESB) ptx::tma_load_2d(b_dst, &tmB, &full[stage], kb * 64, n_tile * BN);
           }
           __syncwarp();
           if (++stage == Cfg::kStages) stage = 0, phase ^= 1;
@@ -210,6 +227,7 @@ k_conv_umma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       constexpr uint32_t idesc = ptx::make_idesc_bf16(kBM, BN);
       int stage = 0;
       uint32_t phase = 0, acc = 0, acc_phase = 0;
+      if (RESB) ptx::mbar_wait(b_full, 0);
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         ptx::mbar_wait(&tempty[acc], acc_phase ^ 1);  // epilogue has drained this accumulator
         ptx::tc_fence_after();
@@ -218,7 +236,8 @@ k_conv_umma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           ptx::mbar_wait(&full[stage], phase);
           ptx::tc_fence_after();
           const uint32_t a_addr = ptx::smem_u32(base + stage * Cfg::kStage);
-          const uint64_t adesc = ptx::make_smem_desc(a_addr, 128), bdesc = ptx::make_smem_desc(a_addr + kABytes, 128);
+          const uint64_t adesc = ptx::make_smem_desc(a_addr, 128);
+          const uint64_t bdesc = ptx::make_smem_desc(RESB ? ptx::smem_u32(resB + kb * Cfg::kBBytes) : a_addr + kABytes, 128);
           if (ptx::elect_one()) {
 #pragma unroll
             for (int k = 0; k < 4; k++)  // 4 x (K = 16) per 64-wide k-block: +32 B = +2 in the descriptor's address field
@@ -312,6 +331,8 @@ __global__ void __launch_bounds__(256) k_avgpool_fc(const __nv_bfloat16* __restr
                                                     const float* __restrict__ fc_b, int num_classes,
                                                     const int* __restrict__ n_dev, int n_base) {
   const int img = blockIdx.x;
+  ptx::pdl_launch_dependents();
+  ptx::pdl_wait();
   if (n_dev && img >= __ldg(n_dev) - n_base) return;
   __shared__ float f[512];
   const __nv_bfloat16* src = in + (int64_t)img * 49 * 512;
@@ -375,6 +396,8 @@ static bool g_use_fused_stem = true;   // HIPAC_FUSED_STEM=0 runs conv1 and the 
 static bool g_fuse_downsample = true; // HIPAC_FUSE_DS=0 runs the 1x1 projection shortcuts as separate kernels
 static bool g_use_row_kernels = true;  // HIPAC_CONV_ROWS=0 forces the im2col kernel everywhere (A/B comparison)
 static bool g_use_cta_pairs = true;    // HIPAC_CTA_PAIRS=0: single-CTA row kernels instead of the cta_group::2 ones
+static bool g_resident_weights = true; // HIPAC_RESIDENT_B=0: the im2col kernel streams the weights of layer2.0.conv1 like everywhere else
+static bool g_tma_epilogue_c128 = true;   // HIPAC_TMA_EPILOGUE_C128=0: the 128-channel residual layer keeps per-thread stores / residual loads
 static bool g_tma_epilogue = true;     // HIPAC_TMA_EPILOGUE=0: 64-channel layers store / fetch the residual per thread (k_conv3x3_rows)
 static bool g_use_cta_pairs_c64 = false;   // HIPAC_CTA_PAIRS_C64=1: CTA pairs for the 64-channel layers too (measured slower)
 
@@ -387,6 +410,8 @@ static void read_env_flags() {
     if (const char* e = getenv("HIPAC_CTA_PAIRS")) g_use_cta_pairs = atoi(e) != 0;
     if (const char* e = getenv("HIPAC_CTA_PAIRS_C64")) g_use_cta_pairs_c64 = atoi(e) != 0;
     if (const char* e = getenv("HIPAC_TMA_EPILOGUE")) g_tma_epilogue = atoi(e) != 0;
+    if (const char* e = getenv("HIPAC_RESIDENT_B")) g_resident_weights = atoi(e) != 0;
+    if (const char* e = getenv("HIPAC_TMA_EPILOGUE_C128")) g_tma_epilogue_c128 = atoi(e) != 0;
     if (const char* e = getenv("HIPAC_FUSED_STEM")) g_use_fused_stem = atoi(e) != 0;
     if (const char* e = getenv("HIPAC_FUSE_DS")) g_fuse_downsample = atoi(e) != 0;
     if (const char* e = getenv("HIPAC_BOUSTROPHEDON")) g_boustrophedon = atoi(e) != 0;
@@ -557,7 +582,8 @@ static int launch_rows_tma_t(const uint8_t* d_packed, const PackedLayout& L, int
   const int grid = p.num_tiles < g_num_sms ? p.num_tiles : g_num_sms;
   {
     ProfileScope ps(name, stream, 2.0 * n * W * W * 64 * 9 * KC * 64);
-    k_conv3x3_rows_tma<KC, W, R><<<grid, conv_threads(64), Cfg::kSmemBytes, stream>>>(tmA, tmB, tmO, tmR, p);
+    HIPAC_CHECK_CUDA(launch_ex(k_conv3x3_rows_tma<KC, W, R>, dim3(grid), dim3(conv_threads(64)), Cfg::kSmemBytes, stream, 1, true, tmA, tmB, tmO,
+                               tmR, p));
   }
   count_launch(1);
   HIPAC_CHECK_CUDA(cudaGetLastError());
@@ -566,11 +592,11 @@ static int launch_rows_tma_t(const uint8_t* d_packed, const PackedLayout& L, int
 
 // CTA-pair row kernel (conv_rows2.cuh).  weights = [BN][9*KC*64 (+ KDS*64)] K-major at w_ptr; ds_in = block input of the
 // fused projection shortcut (KDS = 1) or null.
-template <int BN, int KC, int W, int R, int KDS>
+template <int BN, int KC, int W, int R, int KDS, bool TEPI = (BN == 64)>
 static int launch_rows2_t(const void* w_ptr, const float* bias, const void* in, const void* ds_in, const void* residual, void* out,
                           int n, bool relu, cudaStream_t stream, const char* name, double flops) {
-  using Cfg = Row2Cfg<BN, KC, W, R, KDS>;
-  if (int e = ensure_dyn_smem(k_conv3x3_rows2<BN, KC, W, R, KDS>, Cfg::kSmemBytes)) return e;
+  using Cfg = Row2Cfg<BN, KC, W, R, KDS, TEPI>;
+  if (int e = ensure_dyn_smem(k_conv3x3_rows2<BN, KC, W, R, KDS, TEPI>, Cfg::kSmemBytes)) return e;
   CUtensorMap tmA, tmB, tmA2;
   if (int e = make_region_map(&tmA, in, n, W, W, KC * 64, R)) return e;
   if (int e = make_weight_map(&tmB, w_ptr, BN, (9 * KC + KDS) * 64, BN / 2)) return e;
@@ -581,10 +607,10 @@ static int launch_rows2_t(const void* w_ptr, const float* bias, const void* in, 
   }
   CUtensorMap tmO = tmA, tmR = tmA;
   if (Cfg::kTmaEpi) {
-    if (int e = make_tile_map(&tmO, out, n, W, W, 64, R)) return e;
+    if (int e = make_tile_map(&tmO, out, n, W, W, BN, R)) return e;
     tmR = tmO;
     if (residual)
-      if (int e = make_tile_map(&tmR, residual, n, W, W, 64, R)) return e;
+      if (int e = make_tile_map(&tmR, residual, n, W, W, BN, R)) return e;
   }
   RowConvParams p;
   p.n_img = n, p.num_tiles = n * (W / R), p.relu = relu ? 1 : 0;
@@ -595,16 +621,10 @@ static int launch_rows2_t(const void* w_ptr, const float* bias, const void* in, 
   const int pairs = (p.num_tiles + 1) / 2;
   const int max_pairs = g_num_sms / 2;
   const int grid = 2 * (pairs < max_pairs ? pairs : max_pairs);
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)grid), cfg.blockDim = dim3((unsigned)conv_threads(BN));
-  cfg.dynamicSmemBytes = Cfg::kSmemBytes, cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 2, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr, cfg.numAttrs = 1;
   {
     ProfileScope ps(name, stream, flops);
-    HIPAC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, k_conv3x3_rows2<BN, KC, W, R, KDS>, tmA, tmB, tmA2, tmO, tmR, p));
+    HIPAC_CHECK_CUDA(launch_ex(k_conv3x3_rows2<BN, KC, W, R, KDS, TEPI>, dim3((unsigned)grid), dim3((unsigned)conv_threads(BN)), Cfg::kSmemBytes,
+                               stream, 2, true, tmA, tmB, tmA2, tmO, tmR, p));
   }
   count_launch(1);
   HIPAC_CHECK_CUDA(cudaGetLastError());
@@ -637,23 +657,24 @@ static int run_stem(const uint8_t* d_packed, const PackedLayout& L, const void* 
   const int grid = p.num_blocks < g_num_sms ? p.num_blocks : g_num_sms;
   {
     ProfileScope ps("conv1_pool_fused", stream, 2.0 * n * 112 * 112 * 64 * 147);
-    k_conv1_pool<<<grid, kStemThreads, kStemSmem, stream>>>(tmA, tmB, p);
+    HIPAC_CHECK_CUDA(launch_ex(k_conv1_pool, dim3(grid), dim3(kStemThreads), kStemSmem, stream, 1, true, tmA, tmB, p));
   }
   count_launch(1);
   HIPAC_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
-template <int BN>
+template <int BN, bool RESB = false>
 static int launch_conv_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvParams& p, cudaStream_t stream,
                          const char* name, double flops, const CUtensorMap* tmA2 = nullptr) {
-  using Cfg = ConvCfg<BN>;
-  if (int e = ensure_dyn_smem(k_conv_umma<BN>, Cfg::kSmemBytes)) return e;
+  using Cfg = ConvCfg<BN, RESB>;
+  if (int e = ensure_dyn_smem(k_conv_umma<BN, RESB>, Cfg::kSmemBytes)) return e;
   const int tiles = p.num_m_tiles * p.num_n_tiles;
   const int grid = tiles < g_num_sms ? tiles : g_num_sms;
   {
     ProfileScope ps(name, stream, flops);
-    k_conv_umma<BN><<<grid, conv_threads(BN), Cfg::kSmemBytes, stream>>>(tmA, tmB, tmA2 ? *tmA2 : tmA, p);
+    HIPAC_CHECK_CUDA(launch_ex(k_conv_umma<BN, RESB>, dim3(grid), dim3(conv_threads(BN)), Cfg::kSmemBytes, stream, 1, true, tmA, tmB,
+                               tmA2 ? *tmA2 : tmA, p));
   }
   count_launch(1);
   HIPAC_CHECK_CUDA(cudaGetLastError());
@@ -675,6 +696,9 @@ static int run_conv(const uint8_t* d_packed, const PackedLayout& L, int layer, c
       return launch_rows_t<64, 1, 56, 2, true>(d_packed, L, layer, in, residual, out, n, relu, stream, "conv3x3_c64");
     }
     if (cs.cin == 128 && cs.hin == 28) {
+      if (g_use_cta_pairs && residual && g_tma_epilogue_c128)   // the residual variant: staged epilogue (see conv_rows2.cuh)
+        return launch_rows2_t<128, 2, 28, 4, 0, true>(d_packed + L.w_off[layer], bias, in, nullptr, residual, out, n, relu, stream,
+                                                      "conv3x3_c128", 2.0 * n * 28 * 28 * 128 * 1152);
       if (g_use_cta_pairs)
         return launch_rows2_t<128, 2, 28, 4, 0>(d_packed + L.w_off[layer], bias, in, nullptr, residual, out, n, relu, stream, "conv3x3_c128",
                                                 2.0 * n * 28 * 28 * 128 * 1152);
@@ -716,6 +740,8 @@ static int run_conv(const uint8_t* d_packed, const PackedLayout& L, int layer, c
   const char* name = kNames[gi][cs.k == 1 ? 1 : 0];
   const double flops = 2.0 * p.M_total * cs.cout * K;
   if (bn == 256) return launch_conv_t<256>(tmA, tmB, p, stream, name, flops);
+  if (bn == 128 && g_resident_weights && p.num_n_tiles == 1 && p.num_kb <= ConvCfg<128, true>::kResBlocks)
+    return launch_conv_t<128, true>(tmA, tmB, p, stream, name, flops);      // layer2.0.conv1: the 144 KB of weights stay in shared memory
   return bn == 128 ? launch_conv_t<128>(tmA, tmB, p, stream, name, flops) : launch_conv_t<64>(tmA, tmB, p, stream, name, flops);
 }
 
@@ -966,10 +992,10 @@ static int forward_impl(const void* d_packed, int num_classes, const void* d_bat
       if ((e = conv(l0 + 3, C, nullptr, B, true)) || (e = conv(l0 + 4, B, C, A, true))) return e;
     }
     ProfileScope ps_pool("avgpool_fc", stream, (double)n * (49 * 512 * 2 + 512 * 4));
-    k_avgpool_fc<<<n, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(A), d_feats + (size_t)i0 * 512,
-                                        d_logits ? d_logits + (size_t)i0 * num_classes : nullptr,
-                                        reinterpret_cast<const float*>(pk + L.fc_w_off),
-                                        reinterpret_cast<const float*>(pk + L.fc_b_off), num_classes, g_n_dev, g_n_base);
+    HIPAC_CHECK_CUDA(launch_ex(k_avgpool_fc, dim3(n), dim3(256), 0, stream, 1, true, reinterpret_cast<const __nv_bfloat16*>(A),
+                               d_feats + (size_t)i0 * 512, d_logits ? d_logits + (size_t)i0 * num_classes : nullptr,
+                               reinterpret_cast<const float*>(pk + L.fc_w_off), reinterpret_cast<const float*>(pk + L.fc_b_off),
+                               num_classes, g_n_dev, g_n_base));
     count_launch(1);
   }
   HIPAC_CHECK_CUDA(cudaGetLastError());

@@ -169,6 +169,8 @@ constexpr int kCompactBlock = 1024;
 
 __global__ void __launch_bounds__(kCompactBlock) k_compact_count(const uint8_t* __restrict__ flags, int n_cand, int keep_all,
                                                                 int32_t* __restrict__ block_tot) {
+  ptx::pdl_launch_dependents();
+  ptx::pdl_wait();
   const int idx = blockIdx.x * kCompactBlock + threadIdx.x;
   const int keep = idx < n_cand ? ((flags[idx] & 1) | keep_all) : 0;
   const int n = __syncthreads_count(keep);
@@ -182,6 +184,8 @@ __global__ void __launch_bounds__(kCompactBlock) k_compact(ScanParams p, const u
   __shared__ int warp_tot[32];
   __shared__ int s_base;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  ptx::pdl_launch_dependents();
+  ptx::pdl_wait();
   // ---- survivors in the blocks before this one ----
   int part = 0;
   for (int b = threadIdx.x; b < (int)blockIdx.x; b += kCompactBlock) part += block_tot[b];
@@ -229,10 +233,11 @@ static int launch_compact(const ScanParams& p, const uint8_t* flags, int n_cand,
   const int nb = (n_cand + kCompactBlock - 1) / kCompactBlock;
   ProfileScope ps("compact", stream, (double)n_cand);
   if (nb > 1) {
-    k_compact_count<<<nb, kCompactBlock, 0, stream>>>(flags, n_cand, keep_all, block_tot);
+    HIPAC_CHECK_CUDA(launch_ex(k_compact_count, dim3(nb), dim3(kCompactBlock), 0, stream, 1, true, flags, n_cand, keep_all, block_tot));
     count_launch(1);
   }
-  k_compact<<<nb, kCompactBlock, 0, stream>>>(p, flags, n_cand, d_coords, d_labels, src_idx, d_count, capacity, keep_all, block_tot);
+  HIPAC_CHECK_CUDA(launch_ex(k_compact, dim3(nb), dim3(kCompactBlock), 0, stream, 1, true, p, flags, n_cand, d_coords, d_labels, src_idx, d_count,
+                             capacity, keep_all, (const int32_t*)block_tot));
   count_launch(1);
   return 0;
 }

@@ -158,6 +158,8 @@ __global__ void __launch_bounds__(256) k_cell_stats(ScanParams p, FusedGeom G, i
 // zero, so this is a pure stream: every thread ORs 16-byte chunks (4 independent loads in flight) and only a non-zero
 // chunk touches its cell (cells are multiples of 32 pixels wide, so an aligned 16-byte chunk never straddles two).
 __global__ void __launch_bounds__(256) k_cell_votes(ScanParams p, FusedGeom G, int row0, int nrows) {
+  ptx::pdl_launch_dependents();
+  ptx::pdl_wait();
   const int cpr = (p.W + 15) >> 4;                       // 16-byte chunks per row (the last one may be partial)
   const int64_t total = (int64_t)nrows * cpr;
   const int64_t step = (int64_t)gridDim.x * 256;
@@ -195,6 +197,8 @@ __global__ void __launch_bounds__(256) k_cell_votes(ScanParams p, FusedGeom G, i
 // per-candidate flags from the cell grid
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_patch_flags(ScanParams p, FusedGeom G, uint8_t* __restrict__ flags, int n_cand) {
+  ptx::pdl_launch_dependents();
+  ptx::pdl_wait();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n_cand) return;
   const int ix = idx / p.ny, iyl = idx - ix * p.ny;
@@ -495,6 +499,8 @@ template <bool F1>
 __global__ void __launch_bounds__(128) k_gather(ScanParams p, FusedGeom G, OutParams o, const int32_t* __restrict__ coords,
                                                 const int32_t* __restrict__ count, int capacity) {
   const int slot = blockIdx.x, jp0 = blockIdx.y * kGatherPairs;
+  ptx::pdl_launch_dependents();
+  ptx::pdl_wait();
   if (slot >= min(count[0], capacity)) return;
   HIPAC_DEV_ASSERT(slot < capacity);
   __shared__ uint32_t ring[2 * kGatherPairs][2];   // ring pixels (3 bytes) of the CTA's 16 rows: [row][left, right]
@@ -680,7 +686,7 @@ static int launch_scan_planes_f(const ScanParams& p, const FusedGeom& G, cudaStr
   Z.srow_hi = min(p.H, (G.cy0 + G.ncy) * G.g);
   const int items = Z.n_strips * Z.n_chunks;
   ProfileScope ps("scan_planes", stream, (double)p.H * p.W * 3);
-  k_scan_planes<F><<<(items + kStreamWarps - 1) / kStreamWarps, kStreamWarps * 32, smem, stream>>>(p, G, Z);
+  HIPAC_CHECK_CUDA(launch_ex(k_scan_planes<F>, dim3((items + kStreamWarps - 1) / kStreamWarps), dim3(kStreamWarps * 32), smem, stream, 1, true, p, G, Z));
   count_launch(1);
   return 0;
 }
@@ -722,7 +728,7 @@ static int fused_scan_impl(const ScanParams& p, const OutParams& o, uint8_t* fla
     const int64_t want = (chunks + 1023) / 1024;
     const int grid = (int)(want < 148 * 16 ? want : 148 * 16);
     ProfileScope ps("cell_votes", stream, (double)cell_rows * p.W);
-    k_cell_votes<<<grid, 256, 0, stream>>>(p, G, G.cy0 * G.g, cell_rows);
+    HIPAC_CHECK_CUDA(launch_ex(k_cell_votes, dim3(grid), dim3(256), 0, stream, 1, true, p, G, G.cy0 * G.g, cell_rows));
     count_launch(1);
   } else if (!stream_ok || p.mask) {
     dim3 grid(G.ncx, (cell_rows + 31) / 32);
@@ -732,7 +738,7 @@ static int fused_scan_impl(const ScanParams& p, const OutParams& o, uint8_t* fla
   }
   {
     ProfileScope ps("patch_flags", stream, 0.0);
-    k_patch_flags<<<(n_cand + 255) / 256, 256, 0, stream>>>(p, G, flags, n_cand);
+    HIPAC_CHECK_CUDA(launch_ex(k_patch_flags, dim3((n_cand + 255) / 256), dim3(256), 0, stream, 1, true, p, G, flags, n_cand));
   }
   count_launch(1);
   if (int e = launch_compact(p, flags, n_cand, d_coords, d_labels, src_idx, d_count, capacity, keep_all, block_tot, stream)) return e;
@@ -749,8 +755,8 @@ static int fused_scan_impl(const ScanParams& p, const OutParams& o, uint8_t* fla
     }
     dim3 grid((unsigned)min(n_cand, capacity), OUT / 2 / kGatherPairs);
     ProfileScope ps("gather", stream, 0.0);
-    if (G.f == 1) k_gather<true><<<grid, 128, 0, stream>>>(p, G, o, d_coords, d_count, capacity);
-    else k_gather<false><<<grid, 128, 0, stream>>>(p, G, o, d_coords, d_count, capacity);
+    if (G.f == 1) HIPAC_CHECK_CUDA(launch_ex(k_gather<true>, grid, dim3(128), 0, stream, 1, true, p, G, o, (const int32_t*)d_coords, (const int32_t*)d_count, capacity));
+    else HIPAC_CHECK_CUDA(launch_ex(k_gather<false>, grid, dim3(128), 0, stream, 1, true, p, G, o, (const int32_t*)d_coords, (const int32_t*)d_count, capacity));
     count_launch(1);
   }
   HIPAC_CHECK_CUDA(cudaGetLastError());

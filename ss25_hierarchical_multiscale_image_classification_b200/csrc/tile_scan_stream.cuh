@@ -126,6 +126,8 @@ __global__ void __launch_bounds__(kStreamWarps * 32) k_scan_planes(ScanParams p,
   constexpr int VRND = 1 << (kPrecisionBits - 1);
   extern __shared__ __align__(128) uint8_t sm[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  ptx::pdl_launch_dependents();
+  ptx::pdl_wait();
   const int item = blockIdx.x * kStreamWarps + warp;
   if (item >= Z.n_strips * Z.n_chunks) return;
   const int chunk = item / Z.n_strips, strip = item - chunk * Z.n_strips;

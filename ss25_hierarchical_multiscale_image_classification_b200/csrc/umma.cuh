@@ -19,6 +19,15 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// ---- programmatic dependent launch ----------------------------------------------------------------------------------
+// A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start while its predecessor in the stream
+// is still draining: everything before pdl_wait() (barrier init, TMEM allocation, tensor-map prefetch, loads of the
+// constant weights) overlaps the predecessor's tail; pdl_wait() returns once the predecessor grid has completed and its
+// memory is visible.  EVERY thread of every CTA calls it before touching anything an earlier kernel wrote (and before
+// exiting), so completion of a grid always implies completion of its predecessors.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---- mbarrier ----------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));

@@ -113,13 +113,17 @@ class SurvivorExchange:
     result (no collective)."""
 
     def __init__(self, device, seg_capacity: int, num_classes: int, nx: int, stride: int, segs_per_rank: int = 1, group=None,
-                 with_features: bool = True):
+                 with_features: bool = True, cyclic: bool = False, cyclic_world: int | None = None):
         self.device = torch.device(device)
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.cap, self.k, self.nx, self.stride, self.spr = int(seg_capacity), int(num_classes), int(nx), int(stride), int(segs_per_rank)
         self.fd = 512 if with_features else 0
+        # cyclic: local segment g of rank r is grid-row block g * world + r of the level (block-cyclic sharding: balances
+        # clumped tissue); otherwise every rank owns one contiguous row range and its segments follow each other in y
+        self.cyclic = bool(cyclic)
+        self._cyclic_world = cyclic_world      # tests: emulate the rank-major storage of W ranks inside one process
         l = _lib.lib()
         self.seg_bytes = int(l.hipac_exchange_segment_bytes(self.cap, self.fd, self.k))
         self.nseg = self.world * self.spr
@@ -168,6 +172,7 @@ class SurvivorExchange:
             if self.world > 1:
                 dist.all_gather_into_tensor(self.recv, self.send, group=self.group)
             _lib.check(_lib.lib().hipac_exchange_merge(self.recv.data_ptr(), self.nseg, self.cap, self.fd, self.k, self.stride, self.nx,
+                                                       (self._cyclic_world or self.world) if self.cyclic else 0,
                                                        self.coords.data_ptr(), self.labels.data_ptr(),
                                                        self.features.data_ptr() if self.fd else None,
                                                        self.logits.data_ptr() if self.k else None, self.total.data_ptr(), self.out_cap,

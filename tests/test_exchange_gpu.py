@@ -110,3 +110,49 @@ def test_exchanged_pipelines_equal_single_pass_bitwise():
         r = pipeline.process_level_host(ih, mh, level, packed, pipe, groups=3, exchange=xh)
         for got, want in ((r.coords, ref.coords), (r.labels, ref.labels), (r.features, ref.features), (r.logits, ref.logits)):
             assert torch.equal(got, want.cpu())
+
+
+@pytest.mark.parametrize("world,spr,nx,rows", [(2, 3, 9, 4), (8, 7, 447, 2), (4, 1, 30, 5), (3, 5, 17, 3)])
+def test_block_cyclic_merge_equals_lexsort(world, spr, nx, rows):
+    """Block-cyclic sharding: stored rank-major (as an all-gather delivers the segments), local segment g of rank r is
+    grid-row block g * world + r; the merge must still deliver the whole level in (x, y) order."""
+    from ss25_hierarchical_multiscale_image_classification_b200 import sharding
+    rng = np.random.default_rng(world * 10 + spr)
+    stride, k = 224, 2
+    cap = nx * rows
+    x = sharding.SurvivorExchange("cuda", cap, k, nx, stride, segs_per_rank=world * spr, cyclic=True, cyclic_world=world)
+    allc, alll, allf, allg = [], [], [], []
+    for r in range(world):
+        for g in range(spr):
+            b = g * world + r                                              # global block index = y order
+            xs, ys = np.meshgrid(np.arange(nx) * stride, (b * rows + np.arange(rows)) * stride, indexing="ij")
+            cand = np.stack([xs.ravel(), ys.ravel()], 1).astype(np.int32)
+            keep = rng.random(len(cand)) < (0.0 if (r + g) % 4 == 3 else 0.5)
+            c = cand[keep]
+            n = len(c)
+            lab = rng.integers(0, 2, n).astype(np.uint8)
+            f = rng.standard_normal((n, 512)).astype(np.float32)
+            lg = rng.standard_normal((n, k)).astype(np.float32)
+            # the segment's tensors hold LOCAL coordinates; y_offset moves the block to its place in the level
+            local = c - np.array([0, b * rows * stride], np.int32) + np.array([0, g * rows * stride], np.int32)
+            pad = 2
+            tc = torch.zeros((n + pad, 2), dtype=torch.int32, device="cuda")
+            tc[:n] = torch.from_numpy(local).cuda()
+            tl = torch.zeros((n + pad,), dtype=torch.uint8, device="cuda")
+            tl[:n] = torch.from_numpy(lab).cuda()
+            tf = torch.zeros((n + pad, 512), device="cuda")
+            tf[:n] = torch.from_numpy(f).cuda()
+            tg = torch.zeros((n + pad, k), device="cuda")
+            tg[:n] = torch.from_numpy(lg).cuda()
+            if tc.shape[0] > cap:
+                tc, tl, tf, tg = tc[:cap], tl[:cap], tf[:cap], tg[:cap]
+            x.pack(r * spr + g, tc, tl, tf, tg, torch.tensor([n, 0], dtype=torch.int32, device="cuda"), y_offset=(b - g) * rows * stride)
+            allc.append(c), alll.append(lab), allf.append(f), allg.append(lg)
+    x.merge()
+    out = x.result()
+    allc = np.concatenate(allc)
+    order = np.lexsort((allc[:, 1], allc[:, 0]))
+    assert np.array_equal(out["coords"].cpu().numpy(), allc[order])
+    assert np.array_equal(out["labels"].cpu().numpy(), np.concatenate(alll)[order])
+    assert np.array_equal(out["features"].cpu().numpy(), np.concatenate(allf)[order])
+    assert np.array_equal(out["logits"].cpu().numpy(), np.concatenate(allg)[order])

@@ -73,6 +73,7 @@ def main():
     ap.add_argument("--ranks", type=int, default=None, help="emulated world size when not under torchrun")
     ap.add_argument("--rank", type=int, default=0)
     ap.add_argument("--csv", default=None, help="heatmap: write the CAMELYON16 prob,x,y CSV here (rank 0)")
+    ap.add_argument("--block-rows", type=int, default=8, help="heatmap: grid rows per block of the block-cyclic sharding")
     args = ap.parse_args()
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -108,45 +109,65 @@ def main():
                     "host_generation_s": round(gen_s, 1)})
 
     elif args.what == "heatmap":
-        # configs[3]: P = S = 224 (non-overlapping tiles: explicit stride, level 3 semantics) over a size x size level image
+        # configs[3]: P = S = 224 (non-overlapping tiles: explicit stride, level 3 semantics) over a size x size level image.
+        # Tissue is spatially clumped, so the grid rows are dealt to the ranks BLOCK-CYCLICALLY (blocks of --block-rows grid
+        # rows; with P == S a block needs no halo): rank r holds blocks r, r + N, r + 2N, ... back to back in one local image,
+        # every block is one segment of the exchange step, and the merge kernel knows the cyclic order.
         size = args.size or 100000
         level, S = 3, 224
         P, _ = patch_and_stride(level)
         ny = (size + S - 1) // S
-        i0, i1 = sharding.shard_rows(ny, eff_world, eff_rank)
-        y0, y1 = sharding.slab_rows(i0, i1, S, P, size)
+        nx = (size + S - 1) // S
+        B = max(1, args.block_rows)
+        nblocks = (ny + B - 1) // B
+        spr = (nblocks + eff_world - 1) // eff_world
+        my_blocks = [g * eff_world + eff_rank for g in range(spr) if g * eff_world + eff_rank < nblocks]
+        spans = [(b * B * S, min((b + 1) * B * S, size)) for b in my_blocks]
         t0 = time.perf_counter()
-        img_h, msk_h = host_slab(4321, level, size, size, y0, y1, threads)
+        parts = [host_slab(4321, level, size, size, a, e, threads) for a, e in spans]
         gen_s = time.perf_counter() - t0
-        img, msk = img_h.to(dev), msk_h.to(dev)
-        rows_max = max(sharding.shard_rows(ny, eff_world, r)[1] - sharding.shard_rows(ny, eff_world, r)[0] for r in range(eff_world))
+        img = torch.cat([p_[0] for p_ in parts]).to(dev) if parts else torch.zeros((S, size, 3), dtype=torch.uint8, device=dev)
+        msk = torch.cat([p_[1] for p_ in parts]).to(dev) if parts else torch.zeros((S, size), dtype=torch.uint8, device=dev)
+        del parts
+        local_ny = (int(img.shape[0]) + S - 1) // S
         # the heatmap needs coordinates, labels and logits only: the features stay on their rank
-        xchg = pipeline.exchange_for_level(dev, size, rows_max, S, 2, with_features=False)
+        xchg = sharding.SurvivorExchange(dev, nx * B, 2, nx, S, segs_per_rank=spr, with_features=False, cyclic=True)
 
         def run():
-            n_cand = pipeline.process_level_exchanged(img, msk, level, packed, xchg, stride=S, row_range=(0, i1 - i0), y_offset=y0)
-            g = xchg.result()
-            hm = heatmap.heatmap(g["coords"], g["logits"], size, size, S, fill=0.0)
-            return n_cand, g, hm
+            n_cand = 0
+            for g, b in enumerate(my_blocks):
+                rows = (g * B, min((g + 1) * B, local_ny))
+                seg = pipeline.process_level_enqueue(img, msk, level, packed, stride=S, row_range=rows)
+                xchg.pack(g, seg.pend.coords, seg.pend.labels, seg.features, seg.logits, seg.count, y_offset=(b - g) * B * S)
+                n_cand += nx * (rows[1] - rows[0])
+            for g in range(len(my_blocks), spr):
+                xchg.pack_empty(g)
+            xchg.merge()
+            g_ = xchg.result()
+            hm = heatmap.heatmap(g_["coords"], g_["logits"], size, size, S, fill=0.0)
+            return n_cand, g_, hm
 
         run()   # untimed first pass (allocator warm-up)
         ms, (n_cand, g, hm) = timed(run)
         ms = max_over_ranks(ms, dev)
         n_all = int(g["coords"].shape[0])
-        ys = g["coords"][:, 1]
-        n_mine = int(((ys >= i0 * S) & (ys < i1 * S)).sum())
         import zlib
         hm_np = hm.cpu().numpy()
         crc = zlib.crc32(hm_np.tobytes())
+
+        def rows_of(r):
+            return np.concatenate([np.arange(b * B, min((b + 1) * B, ny)) for b in range(r, nblocks, eff_world)] or [np.zeros(0, np.int64)])
+
+        iy = (g["coords"][:, 1] // S).cpu().numpy()
+        n_mine = int(np.isin(iy, rows_of(eff_rank)).sum())
         # per-shard CRC of the heatmap rows: a real N-rank run prints all N, an emulated rank its own -- they must agree
-        blocks = {}
-        for r in (range(eff_world) if world > 1 else [eff_rank]):
-            a, b = sharding.shard_rows(ny, eff_world, r)
-            blocks[str(r)] = f"{zlib.crc32(np.ascontiguousarray(hm_np[a:b]).tobytes()):08x}"
+        blocks = {str(r): f"{zlib.crc32(np.ascontiguousarray(hm_np[rows_of(r)]).tobytes()):08x}"
+                  for r in (range(eff_world) if world > 1 else [eff_rank])}
         if args.csv and rank == 0:
             heatmap.write_froc_csv(args.csv, g["coords"], g["logits"], level, P, threshold=0.5)
         out.update({"slide": f"{size}x{size} level image, P=S=224", "grid": [int(hm.shape[0]), int(hm.shape[1])],
-                    "rows_of_this_rank": [i0, i1], "candidates_this_rank": n_cand, "survivors_this_rank": n_mine,
+                    "sharding": f"block-cyclic, blocks of {B} grid rows", "blocks_of_this_rank": len(my_blocks),
+                    "candidates_this_rank": n_cand, "survivors_this_rank": n_mine,
                     "survivors_gathered": n_all, "tumor_labelled": int(g["labels"].sum()), "ms": round(ms, 2),
                     "patches_per_s_this_rank" if world == 1 else "patches_per_s": round((n_mine if world == 1 else n_all) / (ms * 1e-3), 1),
                     "candidates_per_s_this_rank": round(n_cand / (ms * 1e-3), 1), "heatmap_sum": float(hm.double().sum()),
