@@ -359,12 +359,17 @@ def run_ours(args):
     conv_ms = sum(v["ms"] for v in conv.values())
     conv_flops = sum(v["work"] for v in conv.values())
     conv_tf = conv_flops / (conv_ms * 1e-3) / 1e12 if conv_ms else 0.0
-    s1 = {k: v for k, v in prof.items() if not k.startswith(("conv", "maxpool", "avgpool", "pack", "exchange"))}
+    conv_tf_short = conv_flops / 2 / (conv_ms_short * 1e-3) / 1e12 if conv_ms_short else 0.0
+    # stage 1 is paired with the (burst, best-of-10) HBM copy figure, so it is taken from the short pass at boost clocks -- round 1's
+    # method; its duration at the step's sustained clocks is reported beside it
+    s1 = {k: v for k, v in prof_short.items() if not k.startswith(("conv", "maxpool", "avgpool", "pack", "exchange"))}
     s1_ms = sum(v["ms"] for v in s1.values()) / 2
+    s1_ms_sustained = sum(v["ms"] for k, v in prof.items() if not k.startswith(("conv", "maxpool", "avgpool", "pack", "exchange"))) / 2
     s1_bytes = img_d.numel() + msk_d.numel() + n_surv * ALGO_OUT_BYTES
     s1_written = n_surv * (S2D_BYTES + 9)                                        # what the kernels really write
     s1_gbs = s1_bytes / (s1_ms * 1e-3) / 1e9 if s1_ms else 0.0
     kernels = {k: {"launches_per_step": v["launches"] // 2, "ms_per_step": round(v["ms"] / 2, 4),
+                   "ms_per_step_boost": round(prof_short[k]["ms"] / 2, 4) if k in prof_short else None,
                    **({"tflops": round(v["work"] / (v["ms"] * 1e-3) / 1e12, 1)} if k.startswith("conv") and v["ms"] else {})}
                for k, v in prof.items()}
 
@@ -422,23 +427,28 @@ def run_ours(args):
         "lesion_mask_device_equals_pillow": mask_equal,
         "roofline": {"bound": "tensor", "kernel": f"conv stack: k_conv1_pool + k_conv3x3_rows + k_conv_umma ({sum(v['launches'] for v in conv.values()) // 2} launches = 20 conv layers per step)",
                      "achieved": round(conv_tf, 1),
-                     "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
-                     "frac": round(conv_tf / peaks["bf16_tflops"], 4),
-                     "peak_note": "burst cuBLAS bf16 figure (the timed region is a fraction of a second); against the sustained "
-                                  f"figure {peaks['bf16_tflops_sustained']} the fraction is {round(conv_tf / peaks['bf16_tflops_sustained'], 4)}",
+                     "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                     "frac": round(conv_tf / peaks["bf16_tflops_sustained"], 4),
+                     "peak_note": "kernels timed inside a long step (sustained, power-capped clocks) against the SUSTAINED cuBLAS bf16 figure, as "
+                                  "the profiling recipe pairs them; the burst pairing -- the same kernels timed in a short 2-step pass at boost "
+                                  "clocks (round 1's method) against the burst figure -- is given in `burst_pairing`",
+                     "burst_pairing": {"achieved": round(conv_tf_short, 1), "peak": peaks["bf16_tflops"],
+                                       "frac": round(conv_tf_short / peaks["bf16_tflops"], 4), "conv_ms_per_step": round(conv_ms_short, 3)},
                      "traffic": traffic.get("conv_dram_bytes_per_step"), "traffic_unit": "DRAM bytes per step over the conv launches",
                      "traffic_source": f"committed ncu capture {traffic.get('file')} ({traffic.get('source')}), not measured in this run",
                      "algorithmic_flops_per_step": conv_flops / 2, "peak_source": peak_src,
                      "conv_ms_per_step": round(conv_ms / 2, 3),
                      "timing_note": f"per-kernel CUDA events over {prof_steps} steps taken right after the timed region, at its sustained "
-                                    "(power-capped) clocks; a 2-step pass after the cooler e2e leg, round 1's method, gives "
-                                    f"{round(conv_ms_short, 3)} ms = {round(conv_flops / 2 / (conv_ms_short * 1e-3) / 1e12, 1) if conv_ms_short else None} TFLOP/s"},
+                                    "(power-capped) clocks"},
         "roofline_stage1": {"bound": "hbm", "kernel": "stage-1 tile scan (all kernels)",
                             "achieved": round(s1_gbs, 1) if s1_ms else None,
                             "peak": peaks["hbm_gbs"], "unit": "GB/s",
                             "frac": round(s1_gbs / peaks["hbm_gbs"], 4) if s1_ms else None,
                             "frac_of_nominal_8TBs": round(s1_gbs / 8000.0, 4) if s1_ms else None,
-                            "ms_per_step": round(s1_ms, 3), "algorithmic_bytes": int(s1_bytes),
+                            "ms_per_step": round(s1_ms, 3), "ms_per_step_at_sustained_clocks": round(s1_ms_sustained, 3),
+                            "timing_note": "kernels timed in a short 2-step pass at boost clocks against the burst (best-of-10) HBM copy figure; inside "
+                                           "the power-capped step the same kernels take ms_per_step_at_sustained_clocks",
+                            "algorithmic_bytes": int(s1_bytes),
                             "algorithmic_bytes_note": "3HW image + HW mask + survivors x (224*224*3*2 + 9) (SURVEY.md 8d)",
                             "written_bytes": int(s1_written),
                             "written_note": "the batch is stored in conv1's S2D16 operand layout (16 of 12 channels, 115 of 112 columns): "
