@@ -76,8 +76,8 @@ k_conv3x3_rows2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     ptx::prefetch_tensormap(&tmA);
     ptx::prefetch_tensormap(&tmB);
     if (KDS) ptx::prefetch_tensormap(&tmA2);
-    for (int s = 0; s < NS; s++) ptx::mbar_init(&a_full[s], 2), ptx::mbar_init(&a_empty[s], 1);
-    ptx::mbar_init(b_full, 2);
+    for (int s = 0; s < NS; s++) ptx::mbar_init(&a_full[s], 1), ptx::mbar_init(&a_empty[s], 1);
+    ptx::mbar_init(b_full, 1);
     for (int a = 0; a < 2; a++) ptx::mbar_init(&tfull[a], 1), ptx::mbar_init(&tempty[a], 8);
     for (int s = 0; s < 4; s++) ptx::mbar_init(&st_ready[s], 1);
     if (Cfg::kTmaEpi) {
@@ -96,8 +96,7 @@ k_conv3x3_rows2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const uint32_t tmem_base = *tmem_slot;
   if (warp == 0) {   // this CTA's half of the resident weights: constant data, loaded before the dependency wait
     if (ptx::elect_one()) {
-      if (leader) ptx::mbar_arrive_expect_tx(b_full, 2 * Cfg::kBBytes);
-      else ptx::mbar_arrive_cluster(b_full, 0);
+      if (leader) ptx::mbar_arrive_expect_tx(b_full, 2 * Cfg::kBBytes);   // the leader alone arms the barrier, for both CTAs' bytes
       for (int kb = 0; kb < Cfg::kNumB; kb++) ptx::tma2_load_2d(sB + kb * Cfg::kBBlock, &tmB, b_full, kb * 64, (int)rank * Cfg::kBHalf);
     }
     __syncwarp();
@@ -126,8 +125,7 @@ k_conv3x3_rows2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         ptx::mbar_wait(&a_empty[sa], pa ^ 1);
         if (ptx::elect_one()) {
           const uint32_t bytes = sl < KC ? Cfg::kLoadBytes : Cfg::kDsLoadBytes;
-          if (leader) ptx::mbar_arrive_expect_tx(&a_full[sa], 2 * bytes);
-          else ptx::mbar_arrive_cluster(&a_full[sa], 0);
+          if (leader) ptx::mbar_arrive_expect_tx(&a_full[sa], 2 * bytes);   // peer bytes may land first: tx-count goes negative, phase stays open
           if (sl < KC) ptx::tma2_load_4d(sA + sa * Cfg::kRegionBytes, &tmA, &a_full[sa], sl * 64, -1, p0 - 1, img);
           else ptx::tma2_load_4d(sA + sa * Cfg::kRegionBytes, &tmA2, &a_full[sa], 0, 0, 2 * p0, img);
         }
