@@ -401,7 +401,7 @@ static bool g_use_cta_pairs_c256 = true;   // HIPAC_CTA_PAIRS_C256=0: layer3 / l
 static bool g_resident_weights = true; // HIPAC_RESIDENT_B=0: the im2col kernel streams the weights of layer2.0.conv1 like everywhere else
 static bool g_tma_epilogue_c128 = true;   // HIPAC_TMA_EPILOGUE_C128=0: the 128-channel residual layer keeps per-thread stores / residual loads
 static bool g_tma_epilogue = true;     // HIPAC_TMA_EPILOGUE=0: 64-channel layers store / fetch the residual per thread (k_conv3x3_rows)
-static bool g_use_cta_pairs_c64 = false;   // HIPAC_CTA_PAIRS_C64=1: CTA pairs for the 64-channel layers too (measured slower)
+static bool g_use_cta_pairs_c64 = true;   // HIPAC_CTA_PAIRS_C64=0: layer1 on single CTAs (k_conv3x3_rows_tma)
 
 // A/B switches for measurements; read once (the workspace size depends on them).
 static bool g_boustrophedon = true;   // alternate the tile order from layer to layer (A/B switch: HIPAC_BOUSTROPHEDON=0)
