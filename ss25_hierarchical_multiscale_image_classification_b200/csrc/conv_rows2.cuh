@@ -126,6 +126,12 @@ k_conv3x3_rows2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         if (ptx::elect_one()) {
           const uint32_t bytes = sl < KC ? Cfg::kLoadBytes : Cfg::kDsLoadBytes;
           if (leader) ptx::mbar_arrive_expect_tx(&a_full[sa], 2 * bytes);   // peer bytes may land first: tx-count goes negative, phase stays open
+          if (Cfg::kTmaEpi && sl == 0 && active && p.residual != nullptr) {
+            // the epilogue's residual tile, pulled into L2 now (NS / SLICES tiles ahead): its staging buffer frees up only one
+            // tile ahead, which is less than a loaded DRAM round trip (the epilogue warps were waiting on st_ready)
+            ptx::tma_prefetch_4d(&tmR, 0, 0, p0, img);
+            if (BN == 128) ptx::tma_prefetch_4d(&tmR, 64, 0, p0, img);
+          }
           if (sl < KC) ptx::tma2_load_4d(sA + sa * Cfg::kRegionBytes, &tmA, &a_full[sa], sl * 64, -1, p0 - 1, img);
           else ptx::tma2_load_4d(sA + sa * Cfg::kRegionBytes, &tmA2, &a_full[sa], 0, 0, 2 * p0, img);
         }
@@ -284,6 +290,12 @@ k_conv3x3_rows2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       bool active;
       const int vt = tile_of(tp, active);
       uint8_t* buf = stage0 + b * Cfg::kStageBytes;
+      // the NEXT tile's residual goes into the other buffer now, a whole group iteration ahead: that buffer's store (end of
+      // the previous iteration) only has to have been read out of shared memory
+      if (gt == 0 && tp + step < num_pairs) {
+        ptx::bulk_wait_group_read<0>();
+        prepare(tp + step, b ^ 1);
+      }
       ptx::mbar_wait(&ready[b], (j >> 1) & 1);
       ptx::mbar_wait(&tfull[acc], acc_phase);
       ptx::tc_fence_after();
@@ -315,11 +327,7 @@ k_conv3x3_rows2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           const int img = vt / TILES_PER_IMG, p0 = (vt - img * TILES_PER_IMG) * R;
           ptx::tma_store_4d(&tmO, buf, 0, 0, p0, img);
         }
-        ptx::bulk_commit_group();                        // (possibly empty) group: keeps the wait_group arithmetic uniform
-        if (tp + step < num_pairs) {
-          ptx::bulk_wait_group_read<1>();
-          prepare(tp + step, b ^ 1);
-        }
+        ptx::bulk_commit_group();
       }
     }
     if (gt == 0) ptx::bulk_wait_group<0>();

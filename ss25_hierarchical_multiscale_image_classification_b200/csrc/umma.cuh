@@ -190,6 +190,13 @@ __device__ __forceinline__ void tma2_load_4d(void* smem_dst, const CUtensorMap* 
       "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(leader_bar) & kPeerBitMask), "r"(c), "r"(w), "r"(h), "r"(n)
       : "memory");
 }
+// L2 prefetch of one TMA box (no shared-memory destination, no barrier): issued a few tiles ahead of the real load so that the
+// latter is an L2 hit
+__device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* m, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];" ::"l"(reinterpret_cast<uint64_t>(m)), "r"(c0),
+               "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
 __device__ __forceinline__ void tma2_load_im2col_4d(void* smem_dst, const CUtensorMap* m, uint64_t* leader_bar, int c, int w, int h, int n,
                                                     uint16_t off_w, uint16_t off_h) {
   asm volatile(
