@@ -136,7 +136,7 @@ struct ConvCfg {
   static constexpr int kBBytes = BN * 128;
   static constexpr int kResBlocks = RESB ? 9 : 0;
   static constexpr int kStage = RESB ? kABytes : kABytes + kBBytes;
-  static constexpr int kStages = RESB ? 4 : (BN == 256 ? 4 : 6);
+  static constexpr int kStages = RESB ? 5 : (BN == 256 ? 4 : 6);
   static constexpr int kTmemCols = 2 * BN;
   static constexpr int kSmemBytes = kStages * kStage + kResBlocks * kBBytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
   static_assert(kSmemBytes <= 232448, "shared memory budget");
@@ -397,6 +397,7 @@ static bool g_use_fused_stem = true;   // HIPAC_FUSED_STEM=0 runs conv1 and the 
 static bool g_fuse_downsample = true; // HIPAC_FUSE_DS=0 runs the 1x1 projection shortcuts as separate kernels
 static bool g_use_row_kernels = true;  // HIPAC_CONV_ROWS=0 forces the im2col kernel everywhere (A/B comparison)
 static bool g_use_cta_pairs = true;    // HIPAC_CTA_PAIRS=0: single-CTA row kernels instead of the cta_group::2 ones
+static bool g_use_cta_pairs_stem = true;   // HIPAC_CTA_PAIRS_STEM=0: the fused stem on single CTAs
 static bool g_use_cta_pairs_c256 = true;   // HIPAC_CTA_PAIRS_C256=0: layer3 / layer4 on single CTAs (k_conv_umma<256>)
 static bool g_resident_weights = true; // HIPAC_RESIDENT_B=0: the im2col kernel streams the weights of layer2.0.conv1 like everywhere else
 static bool g_tma_epilogue_c128 = true;   // HIPAC_TMA_EPILOGUE_C128=0: the 128-channel residual layer keeps per-thread stores / residual loads
@@ -414,6 +415,7 @@ static void read_env_flags() {
     if (const char* e = getenv("HIPAC_TMA_EPILOGUE")) g_tma_epilogue = atoi(e) != 0;
     if (const char* e = getenv("HIPAC_RESIDENT_B")) g_resident_weights = atoi(e) != 0;
     if (const char* e = getenv("HIPAC_CTA_PAIRS_C256")) g_use_cta_pairs_c256 = atoi(e) != 0;
+    if (const char* e = getenv("HIPAC_CTA_PAIRS_STEM")) g_use_cta_pairs_stem = atoi(e) != 0;
     if (const char* e = getenv("HIPAC_TMA_EPILOGUE_C128")) g_tma_epilogue_c128 = atoi(e) != 0;
     if (const char* e = getenv("HIPAC_FUSED_STEM")) g_use_fused_stem = atoi(e) != 0;
     if (const char* e = getenv("HIPAC_FUSE_DS")) g_fuse_downsample = atoi(e) != 0;
@@ -636,7 +638,8 @@ static int launch_rows2_t(const void* w_ptr, const float* bias, const void* in, 
 
 // Fused conv1 + BN + ReLU + maxpool on the S2D16 batch -> [n][56][56][64].
 static int run_stem(const uint8_t* d_packed, const PackedLayout& L, const void* in, void* out, int n, cudaStream_t stream) {
-  if (int e = ensure_dyn_smem(k_conv1_pool, kStemSmem)) return e;
+  const bool pair = g_use_cta_pairs && g_use_cta_pairs_stem;
+  if (int e = pair ? ensure_dyn_smem(k_conv1_pool<true>, kStemSmemPair) : ensure_dyn_smem(k_conv1_pool<false>, kStemSmem)) return e;
   CUtensorMap tmA, tmB;
   {
     cuuint64_t dims[4] = {16, (cuuint64_t)kS2dW, 112, (cuuint64_t)n};
@@ -651,16 +654,20 @@ static int run_stem(const uint8_t* d_packed, const PackedLayout& L, const void* 
       return -5;
     }
   }
-  if (int e = make_weight_map(&tmB, d_packed + L.w_off[0], 64, 256, 64)) return e;
+  if (int e = make_weight_map(&tmB, d_packed + L.w_off[0], 64, 256, pair ? 32 : 64)) return e;
   StemParams p;
   p.num_blocks = n * (56 / kStemPB);
   p.n_dev = g_n_dev, p.n_base = g_n_base, p.reverse = g_reverse;
   p.bias = reinterpret_cast<const float*>(d_packed + L.b_off[0]);
   p.out = reinterpret_cast<__nv_bfloat16*>(out);
-  const int grid = p.num_blocks < g_num_sms ? p.num_blocks : g_num_sms;
+  const int items = pair ? (p.num_blocks + 1) / 2 : p.num_blocks, slots = pair ? g_num_sms / 2 : g_num_sms;
+  const int grid = (pair ? 2 : 1) * (items < slots ? items : slots);
   {
     ProfileScope ps("conv1_pool_fused", stream, 2.0 * n * 112 * 112 * 64 * 147);
-    HIPAC_CHECK_CUDA(launch_ex(k_conv1_pool, dim3(grid), dim3(kStemThreads), kStemSmem, stream, 1, true, tmA, tmB, p));
+    if (pair)
+      HIPAC_CHECK_CUDA(launch_ex(k_conv1_pool<true>, dim3(grid), dim3(kStemThreads), kStemSmemPair, stream, 2, true, tmA, tmB, p));
+    else
+      HIPAC_CHECK_CUDA(launch_ex(k_conv1_pool<false>, dim3(grid), dim3(kStemThreads), kStemSmem, stream, 1, true, tmA, tmB, p));
   }
   count_launch(1);
   HIPAC_CHECK_CUDA(cudaGetLastError());
