@@ -668,7 +668,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--chunk", type=int, default=8192, help="patches per ResNet18 chunk")
     ap.add_argument("--cpu-candidates", type=int, default=96, help="candidates in the bounded CPU-baseline sample")
-    ap.add_argument("--groups", type=int, default=6, help="row groups of the pipelined host->device upload (e2e leg)")
+    ap.add_argument("--groups", type=int, default=12, help="row groups of the pipelined host->device upload (e2e leg)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     if args.impl == "reference":
