@@ -9,20 +9,23 @@
 // M = 256 x N = 256, and each CTA reads 64 B/clk of operands from shared memory instead of 96.
 #pragma once
 
+template <int BN_>
 struct Conv2Cfg {
-  static constexpr int BN = 256;
-  static constexpr int kBHalfBytes = (BN / 2) * 128;          // this CTA's half of one [256 x 64] weight block
-  static constexpr int kStage = kABytes + kBHalfBytes;        // 32 KB
-  static constexpr int kStages = 6;
-  static constexpr int kTmemCols = 2 * BN;                    // 512: the whole TMEM of both SMs
+  static constexpr int BN = BN_;
+  static constexpr int kBHalfBytes = (BN / 2) * 128;          // this CTA's half of one [BN x 64] weight block
+  static constexpr int kStage = kABytes + kBHalfBytes;        // 32 KB (BN = 256) / 24 KB (BN = 128)
+  static constexpr int kStages = BN == 256 ? 6 : 8;           // 192 KB in flight per SM
+  static constexpr int kTmemCols = 2 * BN;                    // BN = 256: the whole TMEM of both SMs
   static constexpr int kSmemBytes = kStages * kStage + 1024 + 256;
 };
 
-__global__ void __launch_bounds__(conv_threads(256), 1)
+// BN = 128 serves layer2.0.conv1 (3x3 / stride 2, 64 -> 128): its single-CTA form keeps the weights resident and has room for
+// only 80 KB of activations in flight per SM, less than HBM latency x bandwidth.
+template <int BN>
+__global__ void __launch_bounds__(conv_threads(BN), 1)
 k_conv_umma2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
              const __grid_constant__ CUtensorMap tmA2, const ConvParams p) {
-  using Cfg = Conv2Cfg;
-  constexpr int BN = Cfg::BN;
+  using Cfg = Conv2Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full = reinterpret_cast<uint64_t*>(base + Cfg::kStages * Cfg::kStage);   // leader

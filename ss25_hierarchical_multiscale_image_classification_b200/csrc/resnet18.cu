@@ -398,6 +398,7 @@ static bool g_fuse_downsample = true; // HIPAC_FUSE_DS=0 runs the 1x1 projection
 static bool g_use_row_kernels = true;  // HIPAC_CONV_ROWS=0 forces the im2col kernel everywhere (A/B comparison)
 static bool g_use_cta_pairs = true;    // HIPAC_CTA_PAIRS=0: single-CTA row kernels instead of the cta_group::2 ones
 static bool g_use_cta_pairs_stem = true;   // HIPAC_CTA_PAIRS_STEM=0: the fused stem on single CTAs
+static bool g_use_cta_pairs_c128_im2col = false;  // HIPAC_CTA_PAIRS_C128_IM2COL=1: layer2.0.conv1 on CTA pairs instead of a single CTA with resident weights (measured 2 % slower)
 static bool g_use_cta_pairs_c256 = true;   // HIPAC_CTA_PAIRS_C256=0: layer3 / layer4 on single CTAs (k_conv_umma<256>)
 static bool g_resident_weights = true; // HIPAC_RESIDENT_B=0: the im2col kernel streams the weights of layer2.0.conv1 like everywhere else
 static bool g_tma_epilogue_c128 = true;   // HIPAC_TMA_EPILOGUE_C128=0: the 128-channel residual layer keeps per-thread stores / residual loads
@@ -416,6 +417,7 @@ static void read_env_flags() {
     if (const char* e = getenv("HIPAC_RESIDENT_B")) g_resident_weights = atoi(e) != 0;
     if (const char* e = getenv("HIPAC_CTA_PAIRS_C256")) g_use_cta_pairs_c256 = atoi(e) != 0;
     if (const char* e = getenv("HIPAC_CTA_PAIRS_STEM")) g_use_cta_pairs_stem = atoi(e) != 0;
+    if (const char* e = getenv("HIPAC_CTA_PAIRS_C128_IM2COL")) g_use_cta_pairs_c128_im2col = atoi(e) != 0;
     if (const char* e = getenv("HIPAC_TMA_EPILOGUE_C128")) g_tma_epilogue_c128 = atoi(e) != 0;
     if (const char* e = getenv("HIPAC_FUSED_STEM")) g_use_fused_stem = atoi(e) != 0;
     if (const char* e = getenv("HIPAC_FUSE_DS")) g_fuse_downsample = atoi(e) != 0;
@@ -691,16 +693,18 @@ static int launch_conv_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const C
   return 0;
 }
 
-// BN = 256 layers on CTA pairs (conv_umma2.cuh); tmB must have been built with a box of BN/2 = 128 weight rows.
+// im2col layers on CTA pairs (conv_umma2.cuh); tmB must have been built with a box of BN/2 weight rows.
+template <int BN>
 static int launch_conv2(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvParams& p, cudaStream_t stream, const char* name,
                         double flops, const CUtensorMap* tmA2 = nullptr) {
-  if (int e = ensure_dyn_smem(k_conv_umma2, Conv2Cfg::kSmemBytes)) return e;
+  using Cfg = Conv2Cfg<BN>;
+  if (int e = ensure_dyn_smem(k_conv_umma2<BN>, Cfg::kSmemBytes)) return e;
   const int ptiles = ((p.num_m_tiles + 1) / 2) * p.num_n_tiles;
   const int max_pairs = g_num_sms / 2;
   const int grid = 2 * (ptiles < max_pairs ? ptiles : max_pairs);
   {
     ProfileScope ps(name, stream, flops);
-    HIPAC_CHECK_CUDA(launch_ex(k_conv_umma2, dim3((unsigned)grid), dim3((unsigned)conv_threads(256)), Conv2Cfg::kSmemBytes, stream, 2, true, tmA,
+    HIPAC_CHECK_CUDA(launch_ex(k_conv_umma2<BN>, dim3((unsigned)grid), dim3((unsigned)conv_threads(BN)), Cfg::kSmemBytes, stream, 2, true, tmA,
                                tmB, tmA2 ? *tmA2 : tmA, p));
   }
   count_launch(1);
@@ -745,7 +749,7 @@ static int run_conv(const uint8_t* d_packed, const PackedLayout& L, int layer, c
   p.num_kb2 = 0, p.stride2 = 1;
   const int bn = cs.cout >= 256 ? 256 : (cs.cout >= 128 ? 128 : 64);
   p.num_n_tiles = cs.cout / bn;
-  const bool pairs256 = bn == 256 && g_use_cta_pairs && g_use_cta_pairs_c256;
+  const bool pairs256 = bn >= 128 && layer != 0 && g_use_cta_pairs && (bn == 256 ? g_use_cta_pairs_c256 : g_use_cta_pairs_c128_im2col);
   CUtensorMap tmA, tmB;
   if (int e = make_weight_map(&tmB, d_packed + L.w_off[layer], cs.cout, K, pairs256 ? bn / 2 : bn)) return e;
   if (layer == 0) {
@@ -767,7 +771,7 @@ static int run_conv(const uint8_t* d_packed, const PackedLayout& L, int layer, c
   const int gi = cs.cout == 64 ? 0 : cs.cout == 128 ? 1 : cs.cout == 256 ? 2 : 3;
   const char* name = kNames[gi][cs.k == 1 ? 1 : 0];
   const double flops = 2.0 * p.M_total * cs.cout * K;
-  if (pairs256) return launch_conv2(tmA, tmB, p, stream, name, flops);
+  if (pairs256) return bn == 256 ? launch_conv2<256>(tmA, tmB, p, stream, name, flops) : launch_conv2<128>(tmA, tmB, p, stream, name, flops);
   if (bn == 256) return launch_conv_t<256>(tmA, tmB, p, stream, name, flops);
   if (bn == 128 && g_resident_weights && p.num_n_tiles == 1 && p.num_kb <= ConvCfg<128, true>::kResBlocks)
     return launch_conv_t<128, true>(tmA, tmB, p, stream, name, flops);      // layer2.0.conv1: the 144 KB of weights stay in shared memory
@@ -809,7 +813,7 @@ static int run_conv_ds_fused(const uint8_t* d_packed, const PackedLayout& L, int
   if (int e = make_im2col_map(&tmA2, block_in, d2)) return e;
   static const char* kNames[3] = {"conv3x3+ds_c128", "conv3x3+ds_c256", "conv3x3+ds_c512"};
   const double flops = 2.0 * p.M_total * cs.cout * fused_gemm_k(s);
-  if (pairs256) return launch_conv2(tmA, tmB, p, stream, kNames[s], flops, &tmA2);
+  if (pairs256) return launch_conv2<256>(tmA, tmB, p, stream, kNames[s], flops, &tmA2);
   return bn == 256 ? launch_conv_t<256>(tmA, tmB, p, stream, kNames[s], flops, &tmA2)
                    : launch_conv_t<128>(tmA, tmB, p, stream, kNames[s], flops, &tmA2);
 }
