@@ -286,6 +286,7 @@ k_conv_umma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #include "conv_rows.cuh"
 #include "conv_rows_tma.cuh"
 #include "conv_rows2.cuh"
+#include "conv_rows2_s2.cuh"
 #include "conv_stem.cuh"
 
 // ==========================================================================================
@@ -399,6 +400,7 @@ static bool g_use_row_kernels = true;  // HIPAC_CONV_ROWS=0 forces the im2col ke
 static bool g_use_cta_pairs = true;    // HIPAC_CTA_PAIRS=0: single-CTA row kernels instead of the cta_group::2 ones
 static bool g_use_cta_pairs_stem = true;   // HIPAC_CTA_PAIRS_STEM=0: the fused stem on single CTAs
 static bool g_use_cta_pairs_c128_im2col = false;  // HIPAC_CTA_PAIRS_C128_IM2COL=1: layer2.0.conv1 on CTA pairs instead of a single CTA with resident weights (measured 2 % slower)
+static bool g_use_s2_rows = true;          // HIPAC_S2_ROWS=0: layer2.0.conv1 through im2col (k_conv_umma<128, RESB>)
 static bool g_use_cta_pairs_c256 = true;   // HIPAC_CTA_PAIRS_C256=0: layer3 / layer4 on single CTAs (k_conv_umma<256>)
 static bool g_resident_weights = true; // HIPAC_RESIDENT_B=0: the im2col kernel streams the weights of layer2.0.conv1 like everywhere else
 static bool g_tma_epilogue_c128 = true;   // HIPAC_TMA_EPILOGUE_C128=0: the 128-channel residual layer keeps per-thread stores / residual loads
@@ -417,6 +419,7 @@ static void read_env_flags() {
     if (const char* e = getenv("HIPAC_RESIDENT_B")) g_resident_weights = atoi(e) != 0;
     if (const char* e = getenv("HIPAC_CTA_PAIRS_C256")) g_use_cta_pairs_c256 = atoi(e) != 0;
     if (const char* e = getenv("HIPAC_CTA_PAIRS_STEM")) g_use_cta_pairs_stem = atoi(e) != 0;
+    if (const char* e = getenv("HIPAC_S2_ROWS")) g_use_s2_rows = atoi(e) != 0;
     if (const char* e = getenv("HIPAC_CTA_PAIRS_C128_IM2COL")) g_use_cta_pairs_c128_im2col = atoi(e) != 0;
     if (const char* e = getenv("HIPAC_TMA_EPILOGUE_C128")) g_tma_epilogue_c128 = atoi(e) != 0;
     if (const char* e = getenv("HIPAC_FUSED_STEM")) g_use_fused_stem = atoi(e) != 0;
@@ -638,6 +641,31 @@ static int launch_rows2_t(const void* w_ptr, const float* bias, const void* in, 
   return 0;
 }
 
+// layer2.0.conv1 (3x3 / stride 2, 64 -> 128, 56x56 -> 28x28) as a parity-split row kernel on CTA pairs (conv_rows2_s2.cuh).
+static int launch_rows2_s2(const void* w_ptr, const float* bias, const void* in, void* out, int n, bool relu, cudaStream_t stream,
+                           const char* name, double flops) {
+  using Cfg = S2Cfg;
+  if (int e = ensure_dyn_smem(k_conv3x3s2_rows2, Cfg::kSmemBytes)) return e;
+  CUtensorMap tmE, tmO, tmB;
+  if (int e = make_strided_map(&tmE, in, n, 56, 56, 64, Cfg::Wp, Cfg::R)) return e;
+  if (int e = make_strided_map(&tmO, in, n, 56, 56, 64, Cfg::Wp, Cfg::R + 1)) return e;
+  if (int e = make_weight_map(&tmB, w_ptr, Cfg::BN, 9 * 64, Cfg::BN / 2)) return e;
+  RowConvParams p;
+  p.n_img = n, p.num_tiles = n * (Cfg::W / Cfg::R), p.relu = relu ? 1 : 0;
+  p.bias = bias, p.residual = nullptr, p.out = reinterpret_cast<__nv_bfloat16*>(out);
+  p.n_dev = g_n_dev, p.n_base = g_n_base, p.reverse = g_reverse;
+  const int pairs = (p.num_tiles + 1) / 2, max_pairs = g_num_sms / 2;
+  const int grid = 2 * (pairs < max_pairs ? pairs : max_pairs);
+  {
+    ProfileScope ps(name, stream, flops);
+    HIPAC_CHECK_CUDA(launch_ex(k_conv3x3s2_rows2, dim3((unsigned)grid), dim3((unsigned)conv_threads(128)), Cfg::kSmemBytes, stream, 2, true, tmE,
+                               tmO, tmB, p));
+  }
+  count_launch(1);
+  HIPAC_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
 // Fused conv1 + BN + ReLU + maxpool on the S2D16 batch -> [n][56][56][64].
 static int run_stem(const uint8_t* d_packed, const PackedLayout& L, const void* in, void* out, int n, cudaStream_t stream) {
   const bool pair = g_use_cta_pairs && g_use_cta_pairs_stem;
@@ -717,6 +745,10 @@ static int run_conv(const uint8_t* d_packed, const PackedLayout& L, int layer, c
                     int n, bool relu, cudaStream_t stream) {
   const ConvSpec& cs = kConvs[layer];
   const int K = conv_gemm_k(layer);
+  if (g_use_row_kernels && g_use_cta_pairs && g_use_s2_rows && cs.k == 3 && cs.stride == 2 && cs.cin == 64 && cs.cout == 128 && cs.hin == 56 &&
+      residual == nullptr)
+    return launch_rows2_s2(d_packed + L.w_off[layer], reinterpret_cast<const float*>(d_packed + L.b_off[layer]), in, out, n, relu, stream,
+                           "conv3x3_c128", 2.0 * n * 28 * 28 * 128 * 576);
   if (g_use_row_kernels && cs.k == 3 && cs.stride == 1) {
     const float* bias = reinterpret_cast<const float*>(d_packed + L.b_off[layer]);
     if (cs.cin == 64 && cs.hin == 56) {
