@@ -425,7 +425,7 @@ def run_ours(args):
         "clocks": clk.summary(),
         "patch_set_crc32": f"{crc:08x}", "patch_set_in_canonical_order": canonical,
         "lesion_mask_device_equals_pillow": mask_equal,
-        "roofline": {"bound": "tensor", "kernel": f"conv stack: k_conv1_pool + k_conv3x3_rows2 + k_conv_umma + k_conv_umma2 ({sum(v['launches'] for v in conv.values()) // 2} launches = 20 conv layers per step)",
+        "roofline": {"bound": "tensor", "kernel": f"conv stack: k_conv1_pool + k_conv3x3_rows2 + k_conv3x3s2_rows2 + k_conv_umma2 ({sum(v['launches'] for v in conv.values()) // 2} launches = 20 conv layers per step)",
                      "achieved": round(conv_tf, 1),
                      "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
                      "frac": round(conv_tf / peaks["bf16_tflops_sustained"], 4),
