@@ -66,7 +66,7 @@ def max_over_ranks(ms, dev):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("what", choices=["pyramid", "heatmap", "batch"])
+    ap.add_argument("what", choices=["c2", "pyramid", "heatmap", "batch"])
     ap.add_argument("--size", type=int, default=None, help="level-0 width = height of the synthetic slide")
     ap.add_argument("--slides", type=int, default=16)
     ap.add_argument("--level", type=int, default=1, help="batch: pyramid level that is tiled")
@@ -90,7 +90,24 @@ def main():
     packed = features.pack_resnet18(seeded_resnet18(seed=0, classifier=True).state_dict(), dev)
     out = {"config": args.what, "n_gpus": world, "emulated_ranks": eff_world if world == 1 else None, "rank": eff_rank if world == 1 else None}
 
-    if args.what == "pyramid":
+    if args.what == "c2":
+        # configs[1] = SURVEY 8d "C2": one 16384 x 16384 level-0 image, P = 1792, with the reference CLI's stride (224: 74 x 74
+        # candidates) AND with non-overlapping patches (stride 1792: 10 x 10 candidates), tile scan + ResNet18 each
+        size = args.size or 16384
+        t0 = time.perf_counter()
+        img, msk = host_slab(1234, 0, size, size, 0, size, threads)
+        gen_s = time.perf_counter() - t0
+        img, msk = img.to(dev), msk.to(dev)
+        runs = {}
+        for S in (224, 1792):
+            fn = lambda S=S: pipeline.process_level(img, msk, 0, packed, stride=S)
+            fn()
+            ms, r = timed(fn)
+            runs[f"stride_{S}"] = {"candidates": r.candidates, "survivors": len(r), "tumor_labelled": int(r.labels.sum()), "ms": round(ms, 3),
+                                   "patches_per_s": round(len(r) / (ms * 1e-3), 1), "candidates_per_s": round(r.candidates / (ms * 1e-3), 1)}
+        out.update({"slide": f"{size}x{size} level-0, P=1792", "host_generation_s": round(gen_s, 1), **runs})
+
+    elif args.what == "pyramid":
         # configs[2]: every level of one slide, reference CLI semantics (stride 224 at every level)
         size = args.size or 32768
         t0 = time.perf_counter()
