@@ -14,7 +14,7 @@
 // Pipeline (per CTA, same shared-memory layout in both):
 //   warp 0  producer: its own tile's region slices by TMA (cta_group::2 form: the bytes are reported to the LEADER's
 //           a_full barrier); waits on its LOCAL a_empty, which the leader's commits reach by multicast
-//   warp 1  leader only: waits a_full (2 arrivals + both CTAs' bytes), issues the UMMAs, commits a_empty / tfull to both
+//   warp 1  leader only: waits a_full (armed by the leader's producer alone, for both CTAs' bytes), issues the UMMAs, commits a_empty / tfull to both
 //           CTAs; in both CTAs it owns the TMEM allocation (cta_group::2 alloc / dealloc are pair-collective)
 //   warps 2.. epilogue: wait the LOCAL tfull, drain their CTA's 128 accumulator rows, arrive on the LEADER's tempty
 #pragma once
