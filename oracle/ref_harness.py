@@ -179,7 +179,8 @@ class _OfflineResNet18Classifier:
         return M()
 
 
-def run_reference_as_written(slide, level: int, stride=None, with_mask: bool = True, seed: int = 0, mask_arr=None):
+def run_reference_as_written(slide, level: int, stride=None, with_mask: bool = True, seed: int = 0, mask_arr=None,
+                             capture_weights: bool = False):
     """The reference's two stages EXACTLY as its CLI runs them, coupled through PNG files on disk:
     ``extract_patches(level=, stride=)`` (src/main.py:609-732, real ``Image.save``) and then
     ``extract_features(level=)`` (src/main.py:805-894: ``PatchDataset`` + ``DataLoader(batch_size=512, num_workers=8)``
@@ -189,7 +190,11 @@ def run_reference_as_written(slide, level: int, stride=None, with_mask: bool = T
     synthetic mask, and ``ResNet18Classifier`` -> ``_OfflineResNet18Classifier`` (see there).  ``torch.manual_seed(seed)``
     is set before ``extract_features`` so its random-init feature model is reproducible.
 
-    Returns dict(stage1_s, stage2_s, n_png, features f32[N,512], labels, paths)."""
+    ``capture_weights``: also return the state dict of the ``ResNet18FeatureExtractor`` that ``extract_features`` built (the
+    class is wrapped by a subclass that records ``state_dict()`` after construction; behaviour unchanged), so that another
+    implementation can be run with the very same random-init weights.
+
+    Returns dict(stage1_s, stage2_s, n_png, features f32[N,512], labels, paths[, weights])."""
     import time
 
     import torch
@@ -205,7 +210,14 @@ def run_reference_as_written(slide, level: int, stride=None, with_mask: bool = T
         return Image.fromarray(mask_arr, "L")
 
     cwd = os.getcwd()
-    orig_parse, orig_cls = ref.parse_xml_mask, ref.ResNet18Classifier
+    orig_parse, orig_cls, orig_fe = ref.parse_xml_mask, ref.ResNet18Classifier, ref.ResNet18FeatureExtractor
+    captured = {}
+
+    class _CapturingFeatureExtractor(orig_fe):
+        def __init__(self, *a, **k):
+            super().__init__(*a, **k)
+            captured["weights"] = {n: v.detach().clone() for n, v in self.state_dict().items()}
+
     out = {}
     with tempfile.TemporaryDirectory() as tmp:
         img_dir = os.path.join(tmp, "data", "camelyon16", "train", "img")
@@ -219,6 +231,8 @@ def run_reference_as_written(slide, level: int, stride=None, with_mask: bool = T
             os.chdir(tmp)
             ref.parse_xml_mask = fake_parse_xml_mask
             ref.ResNet18Classifier = _OfflineResNet18Classifier
+            if capture_weights:
+                ref.ResNet18FeatureExtractor = _CapturingFeatureExtractor
             with contextlib.redirect_stdout(io.StringIO()), contextlib.redirect_stderr(io.StringIO()):
                 t0 = time.perf_counter()
                 ref.extract_patches(level=level, stride=stride)
@@ -239,9 +253,11 @@ def run_reference_as_written(slide, level: int, stride=None, with_mask: bool = T
             else:
                 out["features"], out["labels"], out["paths"] = np.zeros((0, 512), np.float32), np.zeros((0,), np.int64), []
         finally:
-            ref.parse_xml_mask, ref.ResNet18Classifier = orig_parse, orig_cls
+            ref.parse_xml_mask, ref.ResNet18Classifier, ref.ResNet18FeatureExtractor = orig_parse, orig_cls, orig_fe
             os.chdir(cwd)
             _slides.pop(name, None)
+    if capture_weights:
+        out["weights"] = captured.get("weights")
     return out
 
 
