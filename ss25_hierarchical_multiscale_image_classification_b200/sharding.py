@@ -24,6 +24,21 @@ def shard_rows(ny_total: int, world: int, rank: int):
     return i0, i0 + base + (1 if rank < rem else 0)
 
 
+def cyclic_blocks(ny_total: int, world: int, rank: int, block_rows: int):
+    """Block-cyclic sharding of the candidate grid rows: blocks of ``block_rows`` rows are dealt round-robin, rank ``r``
+    owns blocks ``r, r + world, r + 2 world, ...`` (tissue is spatially clumped; contiguous shards of a whole-slide level
+    leave some ranks without a single survivor).  Returns ``(blocks, segs_per_rank)``: ``blocks`` = this rank's
+    ``(block_index, i0, i1)`` grid-row ranges in ascending order, ``segs_per_rank`` = the per-rank block count every rank
+    must present to ``SurvivorExchange(..., cyclic=True)`` (ranks with one block fewer pack an empty segment)."""
+    if not (0 <= rank < world):
+        raise ValueError(f"rank {rank} outside world of {world}")
+    block_rows = max(1, int(block_rows))
+    nblocks = (ny_total + block_rows - 1) // block_rows
+    segs_per_rank = (nblocks + world - 1) // world
+    blocks = [(b, b * block_rows, min((b + 1) * block_rows, ny_total)) for b in range(rank, nblocks, world)]
+    return blocks, segs_per_rank
+
+
 def slab_rows(i0: int, i1: int, stride: int, patch: int, height: int):
     """Level rows ``[y0, y1)`` a rank must hold to tile grid rows ``[i0, i1)``: its own rows plus a
     read-only halo of ``patch - stride`` rows (no inter-GPU halo exchange: the source is the host)."""

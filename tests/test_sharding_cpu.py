@@ -25,6 +25,22 @@ def test_shard_rows_partition_the_grid():
         sharding.shard_rows(10, 2, 2)
 
 
+def test_cyclic_blocks_partition_the_grid_and_agree_on_segment_count():
+    for ny, world, B in [(447, 8, 8), (74, 8, 8), (19, 2, 3), (5, 8, 8), (64, 4, 16), (1, 3, 1), (100, 7, 1)]:
+        seen, spr = [], None
+        for r in range(world):
+            blocks, s = sharding.cyclic_blocks(ny, world, r, B)
+            spr = s if spr is None else spr
+            assert s == spr and spr - 1 <= len(blocks) <= spr                            # every rank presents spr segments (at most one empty)
+            assert [b for b, _, _ in blocks] == list(range(r, (ny + B - 1) // B, world))   # round-robin, ascending
+            for b, i0, i1 in blocks:
+                assert i0 == b * B and 0 < i1 - i0 <= B and i1 <= ny
+                seen += list(range(i0, i1))
+        assert sorted(seen) == list(range(ny))                                           # disjoint cover of the grid rows
+    with pytest.raises(ValueError):
+        sharding.cyclic_blocks(10, 2, 2, 4)
+
+
 def test_slab_rows_cover_every_patch_of_the_shard():
     H, S, P = 16384, 224, 1792
     ny = (H + S - 1) // S

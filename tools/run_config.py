@@ -137,9 +137,9 @@ def main():
         nx = (size + S - 1) // S
         B = max(1, args.block_rows)
         nblocks = (ny + B - 1) // B
-        spr = (nblocks + eff_world - 1) // eff_world
-        my_blocks = [g * eff_world + eff_rank for g in range(spr) if g * eff_world + eff_rank < nblocks]
-        spans = [(b * B * S, min((b + 1) * B * S, size)) for b in my_blocks]
+        blocks, spr = sharding.cyclic_blocks(ny, eff_world, eff_rank, B)
+        my_blocks = [b for b, _, _ in blocks]
+        spans = [(i0 * S, min(i1 * S, size)) for _, i0, i1 in blocks]
         t0 = time.perf_counter()
         parts = [host_slab(4321, level, size, size, a, e, threads) for a, e in spans]
         gen_s = time.perf_counter() - t0
